@@ -1,0 +1,193 @@
+/*
+ * marl_sat_b200.h -- C ABI of the B200-native batched SATEnv hot path.
+ *
+ * This is the drop-in boundary for ONE path of kongqg/marl-sat: the batched
+ * multi-agent SATEnv (reset / flip / clause satisfaction / reward / observation
+ * / auto-reset) and the MAPPO GAE scan that consumes the rollout.  Reference
+ * files (relative to the reference repo root):
+ *     env     = src/envs/multi_agent_sat_env.py
+ *     learner = src/learners/mappo_gnn_sat_learner.py
+ *     runner  = src/runners/mappo_runner.py
+ *
+ * The reference has no FFI of its own (it is pure JAX); the entry points below
+ * are what a `jax.ffi` custom-call layer for this path binds (one handler per
+ * function).  Conventions for every `msat_*` enqueue call:
+ *   - plain pointers and sizes only; every buffer is owned by the caller;
+ *   - all `*_dev` / unqualified data pointers are DEVICE pointers on the current
+ *     device; `stream` is a `cudaStream_t` passed as `void*` (NULL = legacy
+ *     default stream);
+ *   - enqueue-only: no allocation, no synchronisation, no host callbacks; safe to
+ *     capture in a CUDA graph; thread-safe and re-entrant (a plan is immutable);
+ *   - return 0 on success, a negative MSAT_E* code on an argument error (nothing
+ *     is enqueued), a positive value = the `cudaError_t` of a failed launch.
+ *   - there is NO CPU fallback: without a CUDA device every enqueue call fails.
+ *
+ * Data layouts:
+ *   formula bank   P records of `rec_bytes` each: packed u16 literal codes
+ *                  followed by the flat agent-mask bit stream (A*D bits);
+ *   env state      B records of `state_words` u32 each: packed assignment bits,
+ *                  step, problem index, #unsatisfied, done flag;
+ *   observations   int32 [B, A, D], D = 2n+m, values in {-1,0,1}  (env:345-398).
+ */
+#ifndef MARL_SAT_B200_H
+#define MARL_SAT_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MSAT_OK            0
+#define MSAT_EINVAL       -1   /* bad shape / null pointer / out-of-range scalar      */
+#define MSAT_EALIGN       -2   /* a buffer is not aligned as documented               */
+#define MSAT_EUNSUPPORTED -3   /* shape exceeds what one CTA's shared memory can hold */
+
+/* Static description of one SATEnv configuration.  Replaces the constructor
+ * state of `SATEnv.__init__` (env:29-88): agent groups are the reference's
+ * contiguous balanced split (env:294-338), so (n, A) determine agent_vars,
+ * action_mask and variable_to_agent_idx. */
+typedef struct msat_plan msat_plan;
+
+typedef struct msat_dims {
+    int32_t n, m, k;          /* variables, clauses, literals per clause (0-padded)    */
+    int32_t A, V, D;          /* agents, max vars per agent, obs_dim = 2n+m            */
+    int32_t action_mode;      /* 0 single-flip (Discrete(V+1)), 1 multi-flip           */
+    int32_t max_steps;
+    int32_t rec_bytes;        /* bytes per formula-bank record (multiple of 128)       */
+    int32_t state_words;      /* u32 words per env-state record (multiple of 4)        */
+    int32_t group_threads;    /* threads cooperating on one env in the step kernel     */
+    int32_t smem_bytes;       /* dynamic shared memory per CTA of the step kernel      */
+} msat_dims;
+
+/* --- plan (host only, no GPU needed) ------------------------------------- */
+
+/* Replaces SATEnv.__init__/_create_agent_groups (env:29-88, 294-338).
+ * `num_agents` is the value produced by the reference's grouping rule; the
+ * contiguous split base=n/A, rem=n%A is implied.  group_threads = 0 lets the
+ * library choose (32/64/128/256 by observation size). */
+int msat_plan_create(msat_plan** out, int32_t num_vars, int32_t num_clauses, int32_t lits_per_clause,
+                     int32_t num_agents, int32_t action_mode, int32_t max_steps, int32_t group_threads);
+void msat_plan_destroy(msat_plan* plan);
+int msat_plan_dims(const msat_plan* plan, msat_dims* out);
+/* Reference grouping rule (env:294-338): number of agents for (n, vars_per_agent);
+ * vars_per_agent <= 0 means "auto" (n/4 if 4 | n else max(2, floor(sqrt(n)))). */
+int32_t msat_num_agents_for(int32_t num_vars, int32_t vars_per_agent);
+const char* msat_version(void);
+
+/* --- formula bank ---------------------------------------------------------- */
+
+/* Compile P raw formulas (int32 [P, m, k], DIMACS literals, 0 = padding) into bank
+ * records.  Replaces the per-reset work of `_compute_observation_maps` (env:99-128)
+ * and `literal_to_agent_idx` (env:160): the agent/clause and agent/neighbour
+ * relations (including the "-1 == -1" padding quirk) are evaluated once per
+ * formula instead of once per env per step.  `bank` needs P*rec_bytes bytes,
+ * 128-byte aligned. */
+int msat_compile_bank(const msat_plan* plan, const int32_t* clauses, int32_t num_problems,
+                      void* bank, void* stream);
+
+/* --- environment ----------------------------------------------------------- */
+
+/* Replaces `jax.vmap(SATEnv.reset)(clauses[problem_idx], keys)` (env:158-181;
+ * runner:137,295).  problem_idx int32[B] (indices into the bank), keys uint32[B,2]
+ * (legacy JAX PRNG keys).  Writes state[B*state_words] and, if obs != NULL,
+ * obs int32[B,A,D] (16-byte aligned). */
+int msat_reset(const msat_plan* plan, const void* bank, int32_t num_problems,
+               const int32_t* problem_idx, const uint32_t* keys,
+               uint32_t* state, int32_t* obs, int32_t num_envs, void* stream);
+
+/* Replaces `jax.vmap(SATEnv.step_env)` (env:225-284) and, with auto_reset != 0,
+ * the reset-and-select of the rollout loop (learner:422-464) in the same launch.
+ *   actions        int32 [B, A] (mode 0) or [B, A, V] (mode 1)
+ *   state_in/out   may alias (in-place) or differ (functional update)
+ *   new_problem_idx int32[B], reset_keys uint32[B,2]: read only for envs that
+ *                  finish this step and only when auto_reset != 0 (else may be NULL)
+ *   obs            int32 [B, A, D] of the state the caller continues from (the
+ *                  post-reset state for finished envs when auto_reset != 0); NULL = skip
+ *   reward         float [B, A]    (env:183-198: 1.0 when solved else 0.0, all agents)
+ *   done           uint8 [B, done_cols]: the episode-end flag repeated done_cols times per env
+ *                  (A+1 = one per agent plus "__all__", env:260-261; 1 = Transition.global_done
+ *                  only, learner:468); pre-reset values
+ *   solved uint8[B], num_unsatisfied int32[B], episode_step int32[B]  (infos, env:278-282)
+ * Any of reward/done/solved/num_unsatisfied/episode_step may be NULL. */
+int msat_step(const msat_plan* plan, const void* bank, int32_t num_problems,
+              const uint32_t* state_in, uint32_t* state_out, const int32_t* actions,
+              int32_t auto_reset, const int32_t* new_problem_idx, const uint32_t* reset_keys,
+              int32_t* obs, float* reward, uint8_t* done, int32_t done_cols, uint8_t* solved,
+              int32_t* num_unsatisfied, int32_t* episode_step,
+              int32_t num_envs, void* stream);
+
+/* Replaces `SATEnv.get_obs(state)` (env:345-398): obs int32[B,A,D] from a state. */
+int msat_get_obs(const msat_plan* plan, const void* bank, int32_t num_problems,
+                 const uint32_t* state, int32_t* obs, int32_t num_envs, void* stream);
+
+/* Materialise the reference-shaped `SATState` leaves (env:13-24) from packed
+ * state; any output may be NULL.  variable_assignments int32[B,n];
+ * clauses_satisfied_status uint8[B,m]; num_unsatisfied int32[B]; step int32[B];
+ * done uint8[B,A]; clauses int32[B,m,k]; agent_clause_masks int32[B,A,m];
+ * agent_neighbor_masks int32[B,A,n]; literal_to_agent_idx int32[B,m,k];
+ * problem_idx int32[B]. */
+int msat_export_state(const msat_plan* plan, const void* bank, int32_t num_problems,
+                      const uint32_t* state, int32_t num_envs,
+                      int32_t* variable_assignments, uint8_t* clauses_satisfied_status,
+                      int32_t* num_unsatisfied, int32_t* step, uint8_t* done, int32_t* clauses,
+                      int32_t* agent_clause_masks, int32_t* agent_neighbor_masks,
+                      int32_t* literal_to_agent_idx, int32_t* problem_idx, void* stream);
+
+/* Host-buffer convenience wrapper around msat_step for callers that keep actions
+ * and results in (pinned) host memory: copies `actions_host` to `actions_dev`,
+ * steps, copies reward/done/solved/num_unsatisfied/episode_step back into the
+ * `*_host` buffers (each may be NULL) and synchronises the stream.  All device
+ * workspaces are caller-owned.  obs stays on the device (obs_dev). */
+int msat_step_host(const msat_plan* plan, const void* bank, int32_t num_problems,
+                   uint32_t* state, const int32_t* actions_host, int32_t* actions_dev,
+                   int32_t auto_reset, const int32_t* new_problem_idx, const uint32_t* reset_keys,
+                   int32_t* obs_dev, float* reward_dev, uint8_t* done_dev, int32_t done_cols, uint8_t* solved_dev,
+                   int32_t* num_unsatisfied_dev, int32_t* episode_step_dev,
+                   float* reward_host, uint8_t* done_host, uint8_t* solved_host,
+                   int32_t* num_unsatisfied_host, int32_t* episode_step_host,
+                   int32_t num_envs, void* stream);
+
+/* --- rollout RNG chain (JAX 0.4.29 Threefry-2x32, non-partitionable) --------- */
+
+/* One rollout step of the key chain (learner:397,416,426):
+ *   rng,act = split(rng); rng,step = split(rng); rng,prob,reset = split(rng,3).
+ * chain_out uint32[10] = {rng', act_key, step_key, prob_key, reset_key}.
+ * rng_in and chain_out may overlap only if rng_in == chain_out. */
+int msat_rng_chain(const uint32_t* rng_in, uint32_t* chain_out, void* stream);
+
+/* Generic `a, b = jax.random.split(key)` on device: out uint32[4] = {a, b}
+ * (runner:289: `key, _rng = split(key)`). */
+int msat_rng_split2(const uint32_t* key_in, uint32_t* out, void* stream);
+
+/* Per-env derivation for a shard [env_offset, env_offset + num_envs_local) of a
+ * global batch of num_envs_global envs (learner:430,434; runner:291,294):
+ *   problem_idx[b] = randint(prob_key, (B_global,), 0, P)[env_offset + b]
+ *   reset_keys[b]  = split(reset_key, B_global)[env_offset + b]
+ * Uses global indices so every sharding of the batch yields identical values. */
+int msat_env_keys(const uint32_t* prob_key, const uint32_t* reset_key,
+                  int32_t num_envs_global, int32_t env_offset, int32_t num_envs_local,
+                  int32_t num_problems, int32_t* problem_idx, uint32_t* reset_keys, void* stream);
+
+/* --- MAPPO advantage path (learner:504-532) ------------------------------------ */
+
+/* Reverse GAE scan.  reward: float, element (t,b) at reward[t*reward_stride_t +
+ * b*reward_stride_b] (a [T,B,A] buffer passes strides B*A and A: agent 0 is
+ * read, learner:514; a dense team reward [T,B] passes B and 1).  done uint8[T,B],
+ * value float[T,B], last_val float[B] -> advantages, targets float[T,B]. */
+int msat_gae(const float* reward, int64_t reward_stride_t, int64_t reward_stride_b,
+             const uint8_t* done, const float* value, const float* last_val,
+             double gamma, double gae_lambda, float* advantages, float* targets,
+             int32_t num_steps, int32_t num_envs, void* stream);
+
+/* stats double[3] += {count, sum, sum of squares} over adv[0..count).  Zero it
+ * first (msat_adv_stats does NOT clear) so shards can be all-reduced. */
+int msat_adv_stats(const float* adv, int64_t count, double* stats, void* stream);
+/* adv = (adv - mean) / (std + 1e-8), population std, from stats (learner:530-532). */
+int msat_adv_normalize(float* adv, int64_t count, const double* stats, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MARL_SAT_B200_H */

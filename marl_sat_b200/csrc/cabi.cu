@@ -1,0 +1,217 @@
+// extern "C" boundary of libmarlsat_b200.so (include/marl_sat_b200.h): plan construction, argument
+// validation and kernel enqueue.  No allocation, no synchronisation (except msat_step_host, which is
+// documented to synchronise), no torch types.
+#include <math.h>
+#include <new>
+
+#include "../../include/marl_sat_b200.h"
+#include "internal.h"
+
+using namespace msat;
+
+namespace {
+
+inline bool aligned(const void* p, size_t a) { return (reinterpret_cast<uintptr_t>(p) & (a - 1)) == 0; }
+inline int cuda_rc(cudaError_t e) { return e == cudaSuccess ? MSAT_OK : (int)e; }
+constexpr int kMaxSmem = 227 * 1024;
+
+}  // namespace
+
+extern "C" {
+
+const char* msat_version(void) { return "marl_sat_b200 0.1 (sm_100a)"; }
+
+int32_t msat_num_agents_for(int32_t n, int32_t vars_per_agent) {
+    if (n <= 0) return MSAT_EINVAL;
+    if (vars_per_agent > 0) return (n + vars_per_agent - 1) / vars_per_agent;   // env:299
+    if (n % 4 == 0) return n / 4;                                               // env:315-323
+    int r = (int)floor(sqrt((double)n));
+    while ((long long)r * r > n) --r;
+    while ((long long)(r + 1) * (r + 1) <= n) ++r;
+    return r > 2 ? r : 2;                                                       // env:326
+}
+
+int msat_plan_create(msat_plan** out, int32_t n, int32_t m, int32_t k, int32_t A, int32_t action_mode,
+                     int32_t max_steps, int32_t group_threads) {
+    if (!out) return MSAT_EINVAL;
+    *out = nullptr;
+    if (n <= 0 || m <= 0 || k <= 0 || A <= 0 || A > n || n > 32767) return MSAT_EINVAL;
+    if (action_mode != 0 && action_mode != 1) return MSAT_EINVAL;
+    if ((long long)A * (2LL * n + m) > (1LL << 26)) return MSAT_EUNSUPPORTED;
+    msat_plan* p = new (std::nothrow) msat_plan();
+    if (!p) return MSAT_EINVAL;
+    Dims& d = p->d;
+    d.n = n; d.m = m; d.k = k; d.A = A;
+    d.base = n / A; d.rem = n % A;
+    d.V = d.base + (d.rem > 0 ? 1 : 0);
+    d.D = 2 * n + m;
+    d.AD = A * d.D;
+    d.action_mode = action_mode;
+    d.max_steps = max_steps;
+    d.aw = (n + 31) / 32;
+    d.sw = (m + 31) / 32;
+    d.xw = (d.D + 31) / 32 + 1;
+    d.fw = (d.AD + 31) / 32;
+    d.agw = (A + 31) / 32;
+    d.lits_bytes = (m * k * 2 + 15) & ~15;
+    d.rec_bytes = (d.lits_bytes + 4 * (d.fw + 1) + 127) & ~127;
+    d.state_words = (d.aw + 4 + 3) & ~3;
+
+    const int chunks = (d.AD + 3) / 4;
+    int gs = group_threads;
+    if (gs == 0) gs = chunks <= 256 ? 32 : (chunks <= 1024 ? 64 : (chunks <= 2560 ? 128 : 256));
+    if (gs != 32 && gs != 64 && gs != 128 && gs != 256) { delete p; return MSAT_EINVAL; }
+    const GroupLayout L = group_layout(d);
+    // grow the group until one CTA's groups fit in shared memory
+    while (gs < 256 && (long long)L.total * (kCtaThreads / gs) > kMaxSmem) gs *= 2;
+    if ((long long)L.total * (kCtaThreads / gs) > kMaxSmem) { delete p; return MSAT_EUNSUPPORTED; }
+    p->group_threads = gs;
+    p->group_smem_bytes = L.total;
+    p->smem_bytes = L.total * (kCtaThreads / gs);
+    p->compile_smem_bytes = 4 * (m + n) * d.agw;
+    if (p->compile_smem_bytes > kMaxSmem) { delete p; return MSAT_EUNSUPPORTED; }
+    *out = p;
+    return MSAT_OK;
+}
+
+void msat_plan_destroy(msat_plan* plan) { delete plan; }
+
+int msat_plan_dims(const msat_plan* plan, msat_dims* o) {
+    if (!plan || !o) return MSAT_EINVAL;
+    const Dims& d = plan->d;
+    o->n = d.n; o->m = d.m; o->k = d.k; o->A = d.A; o->V = d.V; o->D = d.D;
+    o->action_mode = d.action_mode; o->max_steps = d.max_steps;
+    o->rec_bytes = d.rec_bytes; o->state_words = d.state_words;
+    o->group_threads = plan->group_threads; o->smem_bytes = plan->smem_bytes;
+    return MSAT_OK;
+}
+
+int msat_compile_bank(const msat_plan* plan, const int32_t* clauses, int32_t P, void* bank, void* stream) {
+    if (!plan || P < 0 || (P > 0 && (!clauses || !bank))) return MSAT_EINVAL;
+    if (!aligned(bank, 128) || !aligned(clauses, 4)) return MSAT_EALIGN;
+    return cuda_rc(launch_compile_bank(plan, clauses, P, static_cast<uint8_t*>(bank), (cudaStream_t)stream));
+}
+
+int msat_reset(const msat_plan* plan, const void* bank, int32_t P, const int32_t* problem_idx, const uint32_t* keys,
+               uint32_t* state, int32_t* obs, int32_t B, void* stream) {
+    if (!plan || B < 0 || P <= 0) return MSAT_EINVAL;
+    if (B > 0 && (!bank || !problem_idx || !keys || !state)) return MSAT_EINVAL;
+    if (!aligned(bank, 128) || !aligned(state, 16) || !aligned(obs, 16)) return MSAT_EALIGN;
+    EnvArgs a{};
+    a.bank = static_cast<const uint8_t*>(bank); a.P = P;
+    a.state_out = state; a.prob_idx = problem_idx; a.keys = keys; a.obs = obs; a.B = B;
+    return cuda_rc(launch_env(plan, MODE_RESET, a, (cudaStream_t)stream));
+}
+
+int msat_step(const msat_plan* plan, const void* bank, int32_t P, const uint32_t* state_in, uint32_t* state_out,
+              const int32_t* actions, int32_t auto_reset, const int32_t* new_problem_idx, const uint32_t* reset_keys,
+              int32_t* obs, float* reward, uint8_t* done, int32_t done_cols, uint8_t* solved,
+              int32_t* num_unsatisfied, int32_t* episode_step, int32_t B, void* stream) {
+    if (!plan || B < 0 || P <= 0 || (done && done_cols <= 0)) return MSAT_EINVAL;
+    if (B > 0 && (!bank || !state_in || !state_out || !actions)) return MSAT_EINVAL;
+    if (auto_reset && B > 0 && (!new_problem_idx || !reset_keys)) return MSAT_EINVAL;
+    if (!aligned(bank, 128) || !aligned(state_in, 16) || !aligned(state_out, 16) || !aligned(obs, 16))
+        return MSAT_EALIGN;
+    EnvArgs a{};
+    a.bank = static_cast<const uint8_t*>(bank); a.P = P;
+    a.state_in = state_in; a.state_out = state_out; a.actions = actions;
+    a.auto_reset = auto_reset ? 1 : 0; a.prob_idx = new_problem_idx; a.keys = reset_keys;
+    a.obs = obs; a.reward = reward; a.done = done; a.done_cols = done_cols; a.solved = solved;
+    a.num_unsat = num_unsatisfied; a.episode_step = episode_step; a.B = B;
+    return cuda_rc(launch_env(plan, MODE_STEP, a, (cudaStream_t)stream));
+}
+
+int msat_get_obs(const msat_plan* plan, const void* bank, int32_t P, const uint32_t* state, int32_t* obs, int32_t B,
+                 void* stream) {
+    if (!plan || B < 0 || P <= 0) return MSAT_EINVAL;
+    if (B > 0 && (!bank || !state || !obs)) return MSAT_EINVAL;
+    if (!aligned(bank, 128) || !aligned(state, 16) || !aligned(obs, 16)) return MSAT_EALIGN;
+    EnvArgs a{};
+    a.bank = static_cast<const uint8_t*>(bank); a.P = P;
+    a.state_in = state; a.obs = obs; a.B = B;
+    return cuda_rc(launch_env(plan, MODE_OBS, a, (cudaStream_t)stream));
+}
+
+int msat_export_state(const msat_plan* plan, const void* bank, int32_t P, const uint32_t* state, int32_t B,
+                      int32_t* variable_assignments, uint8_t* clauses_satisfied_status, int32_t* num_unsatisfied,
+                      int32_t* step, uint8_t* done, int32_t* clauses, int32_t* agent_clause_masks,
+                      int32_t* agent_neighbor_masks, int32_t* literal_to_agent_idx, int32_t* problem_idx,
+                      void* stream) {
+    if (!plan || B < 0 || P <= 0) return MSAT_EINVAL;
+    if (B > 0 && (!bank || !state)) return MSAT_EINVAL;
+    ExportArgs a{};
+    a.bank = static_cast<const uint8_t*>(bank); a.P = P; a.state = state; a.B = B;
+    a.assign = variable_assignments; a.sat = clauses_satisfied_status; a.num_unsat = num_unsatisfied;
+    a.step = step; a.done = done; a.clauses = clauses; a.acm = agent_clause_masks; a.anm = agent_neighbor_masks;
+    a.l2a = literal_to_agent_idx; a.pidx = problem_idx;
+    return cuda_rc(launch_export(plan, a, (cudaStream_t)stream));
+}
+
+int msat_step_host(const msat_plan* plan, const void* bank, int32_t P, uint32_t* state, const int32_t* actions_host,
+                   int32_t* actions_dev, int32_t auto_reset, const int32_t* new_problem_idx,
+                   const uint32_t* reset_keys, int32_t* obs_dev, float* reward_dev, uint8_t* done_dev,
+                   int32_t done_cols, uint8_t* solved_dev, int32_t* num_unsatisfied_dev, int32_t* episode_step_dev, float* reward_host,
+                   uint8_t* done_host, uint8_t* solved_host, int32_t* num_unsatisfied_host,
+                   int32_t* episode_step_host, int32_t B, void* stream) {
+    if (!plan || !actions_host || !actions_dev) return MSAT_EINVAL;
+    cudaStream_t s = (cudaStream_t)stream;
+    const Dims& d = plan->d;
+    const size_t act_elems = (size_t)B * d.A * (d.action_mode == 0 ? 1 : d.V);
+    cudaError_t e = cudaMemcpyAsync(actions_dev, actions_host, act_elems * sizeof(int32_t), cudaMemcpyHostToDevice, s);
+    if (e != cudaSuccess) return (int)e;
+    int rc = msat_step(plan, bank, P, state, state, actions_dev, auto_reset, new_problem_idx, reset_keys, obs_dev,
+                       reward_dev, done_dev, done_cols, solved_dev, num_unsatisfied_dev, episode_step_dev, B, stream);
+    if (rc != MSAT_OK) return rc;
+    if (reward_host && reward_dev)
+        e = cudaMemcpyAsync(reward_host, reward_dev, (size_t)B * d.A * sizeof(float), cudaMemcpyDeviceToHost, s);
+    if (e == cudaSuccess && done_host && done_dev)
+        e = cudaMemcpyAsync(done_host, done_dev, (size_t)B * done_cols, cudaMemcpyDeviceToHost, s);
+    if (e == cudaSuccess && solved_host && solved_dev)
+        e = cudaMemcpyAsync(solved_host, solved_dev, (size_t)B, cudaMemcpyDeviceToHost, s);
+    if (e == cudaSuccess && num_unsatisfied_host && num_unsatisfied_dev)
+        e = cudaMemcpyAsync(num_unsatisfied_host, num_unsatisfied_dev, (size_t)B * 4, cudaMemcpyDeviceToHost, s);
+    if (e == cudaSuccess && episode_step_host && episode_step_dev)
+        e = cudaMemcpyAsync(episode_step_host, episode_step_dev, (size_t)B * 4, cudaMemcpyDeviceToHost, s);
+    if (e != cudaSuccess) return (int)e;
+    return cuda_rc(cudaStreamSynchronize(s));
+}
+
+int msat_rng_chain(const uint32_t* rng_in, uint32_t* chain_out, void* stream) {
+    if (!rng_in || !chain_out) return MSAT_EINVAL;
+    return cuda_rc(launch_rng_chain(rng_in, chain_out, (cudaStream_t)stream));
+}
+
+int msat_rng_split2(const uint32_t* key_in, uint32_t* out, void* stream) {
+    if (!key_in || !out) return MSAT_EINVAL;
+    return cuda_rc(launch_rng_split2(key_in, out, (cudaStream_t)stream));
+}
+
+int msat_env_keys(const uint32_t* prob_key, const uint32_t* reset_key, int32_t Bg, int32_t off, int32_t Bl, int32_t P,
+                  int32_t* problem_idx, uint32_t* reset_keys, void* stream) {
+    if (Bg < 0 || off < 0 || Bl < 0 || (long long)off + Bl > Bg) return MSAT_EINVAL;
+    if (problem_idx && (!prob_key || P <= 0)) return MSAT_EINVAL;
+    if (reset_keys && !reset_key) return MSAT_EINVAL;
+    if (Bg > (1 << 30)) return MSAT_EUNSUPPORTED;
+    return cuda_rc(launch_env_keys(prob_key, reset_key, Bg, off, Bl, P, problem_idx, reset_keys, (cudaStream_t)stream));
+}
+
+int msat_gae(const float* reward, int64_t rs_t, int64_t rs_b, const uint8_t* done, const float* value,
+             const float* last_val, double gamma, double gae_lambda, float* advantages, float* targets, int32_t T,
+             int32_t B, void* stream) {
+    if (T < 0 || B < 0) return MSAT_EINVAL;
+    if (T > 0 && B > 0 && (!reward || !done || !value || !last_val || !advantages || !targets)) return MSAT_EINVAL;
+    return cuda_rc(launch_gae(reward, rs_t, rs_b, done, value, last_val, (float)gamma, (float)(gamma * gae_lambda),
+                              advantages, targets, T, B, (cudaStream_t)stream));
+}
+
+int msat_adv_stats(const float* adv, int64_t count, double* stats, void* stream) {
+    if (count < 0 || !stats || (count > 0 && !adv)) return MSAT_EINVAL;
+    return cuda_rc(launch_adv_stats(adv, count, stats, (cudaStream_t)stream));
+}
+
+int msat_adv_normalize(float* adv, int64_t count, const double* stats, void* stream) {
+    if (count < 0 || !stats || (count > 0 && !adv)) return MSAT_EINVAL;
+    return cuda_rc(launch_adv_normalize(adv, count, stats, (cudaStream_t)stream));
+}
+
+}  // extern "C"

@@ -1,0 +1,130 @@
+// Shared device helpers for the SATEnv kernels (sm_100a).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace msat {
+
+// Device-side view of a plan; passed by value to every kernel.
+struct Dims {
+    int n, m, k, A, V, D, AD;
+    int action_mode, max_steps;
+    int base, rem;        // contiguous balanced grouping: size_a = base + (a < rem)
+    int aw, sw, xw, fw;   // words: assignment, clause status, obs value vector (+1 pad), flat mask stream
+    int lits_bytes;       // padded byte size of the literal-code block inside a bank record
+    int rec_bytes;        // bank record size (multiple of 128)
+    int state_words;      // env-state record words (multiple of 4)
+    int agw;              // words of an agent bit-set = ceil(A/32)
+};
+
+// State record word offsets (after the aw assignment words).
+enum { ST_STEP = 0, ST_PIDX = 1, ST_NUNSAT = 2, ST_FLAGS = 3 };
+
+constexpr uint16_t LIT_PAD = 0xFFFFu;   // literal code of a 0-padding literal (never true)
+
+// ---- agent grouping (env:294-338; contiguous balanced split) --------------
+__host__ __device__ __forceinline__ int group_size(const Dims& d, int a) { return d.base + (a < d.rem ? 1 : 0); }
+__host__ __device__ __forceinline__ int group_start(const Dims& d, int a) { return a * d.base + (a < d.rem ? a : d.rem); }
+__host__ __device__ __forceinline__ int var_to_agent(const Dims& d, int v) {
+    const int big = d.rem * (d.base + 1);
+    return v < big ? v / (d.base + 1) : d.rem + (v - big) / d.base;
+}
+
+// ---- Threefry-2x32 (JAX 0.4.29 default PRNG; oracle/threefry.py) ---------
+__host__ __device__ __forceinline__ uint32_t rotl32(uint32_t x, int r) { return (x << r) | (x >> (32 - r)); }
+
+__host__ __device__ __forceinline__ void threefry2x32(uint32_t k0, uint32_t k1, uint32_t& x0, uint32_t& x1) {
+    const uint32_t ks[3] = {k0, k1, k0 ^ k1 ^ 0x1BD11BDAu};
+    x0 += ks[0];
+    x1 += ks[1];
+#define MSAT_TF_ROUND(r) x0 += x1; x1 = rotl32(x1, r); x1 ^= x0;
+#define MSAT_TF_A MSAT_TF_ROUND(13) MSAT_TF_ROUND(15) MSAT_TF_ROUND(26) MSAT_TF_ROUND(6)
+#define MSAT_TF_B MSAT_TF_ROUND(17) MSAT_TF_ROUND(29) MSAT_TF_ROUND(16) MSAT_TF_ROUND(24)
+    MSAT_TF_A x0 += ks[1]; x1 += ks[2] + 1u;
+    MSAT_TF_B x0 += ks[2]; x1 += ks[0] + 2u;
+    MSAT_TF_A x0 += ks[0]; x1 += ks[1] + 3u;
+    MSAT_TF_B x0 += ks[1]; x1 += ks[2] + 4u;
+    MSAT_TF_A x0 += ks[2]; x1 += ks[0] + 5u;
+#undef MSAT_TF_A
+#undef MSAT_TF_B
+#undef MSAT_TF_ROUND
+}
+
+// Element i of threefry_2x32(key, arange(N)) (jax._src.prng.threefry_2x32 with
+// the odd-length zero pad): first half of the counters feeds word 0, second half word 1.
+__host__ __device__ __forceinline__ uint32_t bits32_at(uint32_t k0, uint32_t k1, uint32_t N, uint32_t i) {
+    const uint32_t half = (N + 1u) >> 1;
+    const bool lo = i < half;
+    const uint32_t blk = lo ? i : i - half;
+    uint32_t x0 = blk;
+    uint32_t x1 = (half + blk < N) ? half + blk : 0u;   // the pad counter is 0
+    threefry2x32(k0, k1, x0, x1);
+    return lo ? x0 : x1;
+}
+
+// a, b = jax.random.split(key): counters [0,1,2,3] -> blocks (0,2),(1,3); a = {x0(0), x0(1)}, b = {x1(0), x1(1)}.
+__host__ __device__ __forceinline__ void split2(uint32_t k0, uint32_t k1, uint32_t a[2], uint32_t b[2]) {
+    uint32_t p0 = 0u, p1 = 2u, q0 = 1u, q1 = 3u;
+    threefry2x32(k0, k1, p0, p1);
+    threefry2x32(k0, k1, q0, q1);
+    a[0] = p0; a[1] = q0; b[0] = p1; b[1] = q1;
+}
+
+// ---- bit-stream helpers ------------------------------------------------------
+// 32 bits starting at bit `pos` of a clean little-endian bit array of `nwords` words
+// (bits past the logical end are zero; reads outside the array return zero).  pos may be negative.
+__device__ __forceinline__ uint32_t ldw(const uint32_t* a, int i, int nwords) {
+    return (i >= 0 && i < nwords) ? a[i] : 0u;
+}
+__device__ __forceinline__ uint32_t extract32(const uint32_t* a, int nwords, int pos) {
+    const int w = pos >> 5;             // arithmetic shift: floor for negatives
+    const int sh = pos & 31;
+    const uint32_t lo = ldw(a, w, nwords);
+    const uint32_t hi = ldw(a, w + 1, nwords);
+    return __funnelshift_r(lo, hi, sh);
+}
+
+// ---- mbarrier + TMA bulk copy (global -> shared) --------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    do {
+        asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+            "selp.u32 %0, 1, 0, p;\n"
+            "}\n"
+            : "=r"(ok)
+            : "r"(smem_u32(bar)), "r"(parity)
+            : "memory");
+    } while (!ok);
+}
+// 1-D bulk copy through the TMA engine; bytes % 16 == 0, both addresses 16-byte aligned.
+__device__ __forceinline__ void tma_load_1d(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(smem_dst)),
+                 "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// Barrier over the GS threads that cooperate on one env.
+template <int GS>
+__device__ __forceinline__ void group_sync(int gid) {
+    if constexpr (GS == 32) {
+        __syncwarp();
+    } else {
+        asm volatile("bar.sync %0, %1;" ::"r"(gid + 1), "n"(GS) : "memory");
+    }
+}
+
+}  // namespace msat

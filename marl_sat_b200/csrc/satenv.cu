@@ -1,0 +1,452 @@
+// Batched SATEnv kernels for sm_100a: formula-bank compiler, reset / step(+auto-reset) / get_obs,
+// and the SATState exporter.  Reference semantics: src/envs/multi_agent_sat_env.py (cited as env:LINE)
+// and src/learners/mappo_gnn_sat_learner.py:422-464 (auto-reset).  See DESIGN.md section 4.
+#include "internal.h"
+
+namespace msat {
+
+// =====================================================================================
+// K_compile: one CTA per formula.  Evaluates the agent<->clause and agent<->neighbour
+// relations of _compute_observation_maps (env:99-128) once per formula and stores them as a
+// flat A*D-bit mask stream in observation order [own(n) | clauses(m) | neighbours(n)] per agent,
+// next to the literals packed as u16 codes ((var << 1) | negated, 0xFFFF for a 0 padding literal).
+// =====================================================================================
+__global__ void __launch_bounds__(256) compile_bank_kernel(Dims d, const int32_t* __restrict__ clauses,
+                                                           uint8_t* __restrict__ bank) {
+    extern __shared__ uint32_t csm[];
+    uint32_t* clause_agents = csm;                 // [m][agw]  agents related to clause c
+    uint32_t* var_agents = csm + d.m * d.agw;      // [n][agw]  agents that see variable v in a related clause
+    const int tid = threadIdx.x, nt = blockDim.x;
+    const int32_t* cl = clauses + (size_t)blockIdx.x * d.m * d.k;
+    uint8_t* rec = bank + (size_t)blockIdx.x * d.rec_bytes;
+    uint16_t* lits = reinterpret_cast<uint16_t*>(rec);
+    uint32_t* mflat = reinterpret_cast<uint32_t*>(rec + d.lits_bytes);
+
+    for (int i = tid; i < (d.m + d.n) * d.agw; i += nt) csm[i] = 0u;
+    for (int i = d.m * d.k + tid; i < d.lits_bytes / 2; i += nt) lits[i] = LIT_PAD;
+    for (int i = d.lits_bytes / 4 + d.fw + 1 + tid; i < d.rec_bytes / 4; i += nt)
+        reinterpret_cast<uint32_t*>(rec)[i] = 0u;
+    __syncthreads();
+
+    for (int c = tid; c < d.m; c += nt) {
+        uint32_t* ca = clause_agents + c * d.agw;
+        for (int j = 0; j < d.k; ++j) {
+            const int lit = cl[c * d.k + j];
+            uint16_t code;
+            if (lit == 0) {
+                // env:100,106: |0|-1 = -1 equals the -1 padding of every agent that owns fewer than
+                // V variables, so the clause becomes "related" to all of those agents.
+                code = LIT_PAD;
+                if (d.rem > 0)
+                    for (int a = d.rem; a < d.A; ++a) ca[a >> 5] |= 1u << (a & 31);
+            } else {
+                int v = (lit < 0 ? -lit : lit) - 1;
+                v = v < d.n ? v : d.n - 1;
+                code = (uint16_t)((v << 1) | (lit < 0 ? 1 : 0));
+                const int a = var_to_agent(d, v);
+                ca[a >> 5] |= 1u << (a & 31);
+            }
+            lits[c * d.k + j] = code;
+        }
+    }
+    __syncthreads();
+    // env:116-121: every real variable of a related clause is a candidate neighbour.
+    for (int c = tid; c < d.m; c += nt) {
+        for (int j = 0; j < d.k; ++j) {
+            const uint16_t code = lits[c * d.k + j];
+            if (code == LIT_PAD) continue;
+            const int v = code >> 1;
+            for (int w = 0; w < d.agw; ++w) {
+                const uint32_t x = clause_agents[c * d.agw + w];
+                if (x) atomicOr(&var_agents[v * d.agw + w], x);
+            }
+        }
+    }
+    __syncthreads();
+    for (int w = tid; w < d.fw + 1; w += nt) {
+        uint32_t bits = 0u;
+        for (int b = 0; b < 32; ++b) {
+            const int j = w * 32 + b;
+            if (j >= d.AD) break;
+            const int a = j / d.D, p = j - a * d.D;
+            uint32_t bit;
+            if (p < d.n) {
+                bit = var_to_agent(d, p) == a;                                         // env:355
+            } else if (p < d.n + d.m) {
+                bit = (clause_agents[(p - d.n) * d.agw + (a >> 5)] >> (a & 31)) & 1u;  // env:112
+            } else {
+                const int v = p - d.n - d.m;
+                bit = ((var_agents[v * d.agw + (a >> 5)] >> (a & 31)) & 1u) && var_to_agent(d, v) != a;   // env:123
+            }
+            bits |= bit << b;
+        }
+        mflat[w] = bits;
+    }
+}
+
+// =====================================================================================
+// Device pieces of the env kernel.  One group of GS threads owns one env.
+// =====================================================================================
+
+// Clause truth via warp ballots (env:130-156): lane = clause, ballot word = 32 clause-status bits.
+template <int GS>
+__device__ __forceinline__ void eval_clauses(const Dims& d, const uint16_t* lits, const uint32_t* assign,
+                                             uint32_t* satw, int* nunsat, int gt) {
+    const int lane = gt & 31;
+    int local = 0;
+    for (int w = gt >> 5; w < d.sw; w += GS / 32) {
+        const int c = w * 32 + lane;
+        const bool valid = c < d.m;
+        bool sat = false;
+        if (valid) {
+            const uint16_t* L = lits + c * d.k;
+            for (int j = 0; j < d.k; ++j) {
+                const uint32_t code = L[j];
+                if (code != LIT_PAD) {
+                    const uint32_t v = code >> 1;
+                    sat |= (((assign[v >> 5] >> (v & 31)) ^ code) & 1u) != 0u;   // true <=> assignment bit != negation flag
+                }
+            }
+        }
+        const uint32_t word = __ballot_sync(0xffffffffu, valid && sat);
+        const uint32_t bad = __ballot_sync(0xffffffffu, valid && !sat);
+        if (lane == 0) {
+            satw[w] = word;
+            local += __popc(bad);
+        }
+    }
+    if (lane == 0 && local) atomicAdd(nunsat, local);
+}
+
+// assign = randint(key, (n,), 0, 2) (env:162): bit 0 of threefry_2x32(split(key)[1], arange(n)).
+template <int GS>
+__device__ __forceinline__ void threefry_assign(const Dims& d, uint32_t k0, uint32_t k1, uint32_t* assign, int gt) {
+    uint32_t ka[2], kb[2];
+    split2(k0, k1, ka, kb);
+    const int half = (d.n + 1) >> 1;
+    for (int i = gt; i < half; i += GS) {
+        uint32_t x0 = (uint32_t)i;
+        uint32_t x1 = (half + i < d.n) ? (uint32_t)(half + i) : 0u;
+        threefry2x32(kb[0], kb[1], x0, x1);
+        if (x0 & 1u) atomicOr(&assign[i >> 5], 1u << (i & 31));
+        const int v = half + i;
+        if (v < d.n && (x1 & 1u)) atomicOr(&assign[v >> 5], 1u << (v & 31));
+    }
+}
+
+// Apply all agents' flips simultaneously (env:233-250) on the packed assignment in shared memory.
+template <int GS>
+__device__ __forceinline__ void apply_actions(const Dims& d, const int32_t* __restrict__ actions, int e,
+                                              uint32_t* assign, int gt) {
+    if (d.action_mode == 0) {
+        const int32_t* act = actions + (size_t)e * d.A;
+        for (int a = gt; a < d.A; a += GS) {
+            const int x = act[a];
+            const int size = group_size(d, a);
+            if (x >= size) continue;                       // env:236 no-op
+            int idx = x < size - 1 ? x : size - 1;         // env:238
+            if (idx < 0) idx += d.V;                       // JAX gather: wrap once, then clamp
+            idx = idx < 0 ? 0 : (idx > d.V - 1 ? d.V - 1 : idx);
+            if (idx >= size) continue;                     // landed on a -1 pad: one_hot(-1) = 0 (env:243)
+            const int v = group_start(d, a) + idx;
+            atomicXor(&assign[v >> 5], 1u << (v & 31));
+        }
+    } else {
+        const int32_t* act = actions + (size_t)e * d.A * d.V;
+        for (int i = gt; i < d.A * d.V; i += GS) {
+            const int a = i / d.V, j = i - a * d.V;
+            if (j < group_size(d, a) && (act[i] & 1)) {    // env:246-250 (actions are 0/1)
+                const int v = group_start(d, a) + j;
+                atomicXor(&assign[v >> 5], 1u << (v & 31));
+            }
+        }
+    }
+}
+
+// Observation writer (env:345-398).  Per env the A*D output ints are one flat range of the
+// [B,A,D] tensor.  out[i] = mask[i] ? value[i] : -1 where mask is the bank's flat bit stream and
+// value is [assign | clause status | assign] repeated per agent.  Both streams are re-based to the
+// 128-byte aligned start of the range so every lane owns whole 16-byte chunks (st.global.cs.v4).
+template <int GS>
+__device__ __forceinline__ void emit_obs(const Dims& d, int e, const uint32_t* assign, const uint32_t* satw,
+                                         uint32_t* X, uint2* smx, const uint32_t* mflat,
+                                         int32_t* __restrict__ obs, int gid, int gt) {
+    for (int w = gt; w < d.xw; w += GS) {
+        const int pos = 32 * w;
+        X[w] = extract32(assign, d.aw, pos) | extract32(satw, d.sw, pos - d.n) |
+               extract32(assign, d.aw, pos - d.n - d.m);
+    }
+    group_sync<GS>(gid);
+
+    const long long g_start = (long long)e * d.AD;
+    const int s = (int)(g_start & 31);
+    const int nw = (s + d.AD + 31) >> 5;
+    for (int w = gt; w < nw; w += GS) {
+        const int j0 = 32 * w - s;
+        const uint32_t mw = extract32(mflat, d.fw + 1, j0);
+        uint32_t xw = 0u;
+        int j = j0 > 0 ? j0 : 0;
+        const int jend = (j0 + 32 < d.AD) ? j0 + 32 : d.AD;
+        if (j < jend) {
+            int p = j - (j / d.D) * d.D;
+            while (j < jend) {
+                int len = d.D - p;
+                if (len > jend - j) len = jend - j;
+                uint32_t bits = extract32(X, d.xw, p);
+                if (len < 32) bits &= (1u << len) - 1u;
+                xw |= bits << (j - j0);
+                j += len;
+                p = 0;
+            }
+        }
+        smx[w] = make_uint2(mw, xw);
+    }
+    group_sync<GS>(gid);
+
+    int32_t* out = obs + (g_start - s);
+    const int lo_valid = s, hi_valid = s + d.AD;
+    const int nchunks = (hi_valid + 3) >> 2;
+#pragma unroll 4
+    for (int q = gt; q < nchunks; q += GS) {
+        const uint2 mx = smx[q >> 3];
+        const int sh = (q & 7) * 4;
+        const uint32_t mn = mx.x >> sh, xn = mx.y >> sh;
+        int4 v;
+        v.x = (mn & 1u) ? (int)(xn & 1u) : -1;
+        v.y = (mn & 2u) ? (int)((xn >> 1) & 1u) : -1;
+        v.z = (mn & 4u) ? (int)((xn >> 2) & 1u) : -1;
+        v.w = (mn & 8u) ? (int)((xn >> 3) & 1u) : -1;
+        const int lo = 4 * q;
+        if (lo >= lo_valid && lo + 4 <= hi_valid) {
+            __stcs(reinterpret_cast<int4*>(out + lo), v);
+        } else {
+            if (lo + 0 >= lo_valid && lo + 0 < hi_valid) out[lo + 0] = v.x;
+            if (lo + 1 >= lo_valid && lo + 1 < hi_valid) out[lo + 1] = v.y;
+            if (lo + 2 >= lo_valid && lo + 2 < hi_valid) out[lo + 2] = v.z;
+            if (lo + 3 >= lo_valid && lo + 3 < hi_valid) out[lo + 3] = v.w;
+        }
+    }
+}
+
+// =====================================================================================
+// K_env<GS, MODE>: reset / step (+ fused auto-reset) / get_obs.  256-thread CTAs, 256/GS envs each.
+// =====================================================================================
+template <int GS, int MODE>
+__global__ void __launch_bounds__(kCtaThreads) env_kernel(const Dims d, const EnvArgs a) {
+    extern __shared__ __align__(128) uint8_t smem_raw[];
+    const int gid = threadIdx.x / GS, gt = threadIdx.x % GS;
+    const int e = blockIdx.x * (kCtaThreads / GS) + gid;
+    if (e >= a.B) return;   // whole group leaves together
+
+    const GroupLayout L = group_layout(d);
+    uint8_t* base = smem_raw + (size_t)gid * L.total;
+    uint8_t* rec = base + L.rec;
+    uint32_t* st = reinterpret_cast<uint32_t*>(base + L.st);
+    uint32_t* satw = reinterpret_cast<uint32_t*>(base + L.satw);
+    uint32_t* X = reinterpret_cast<uint32_t*>(base + L.x);
+    uint2* smx = reinterpret_cast<uint2*>(base + L.smx);
+    uint64_t* bar = reinterpret_cast<uint64_t*>(base + L.bar);
+    int* misc = reinterpret_cast<int*>(base + L.misc);
+    const uint16_t* lits = reinterpret_cast<const uint16_t*>(rec);
+    const uint32_t* mflat = reinterpret_cast<const uint32_t*>(rec + d.lits_bytes);
+    uint32_t* st_tail = st + d.aw;
+
+    // ---- stage inputs: state record (plain loads) and bank record (TMA bulk copy) ----
+    if (MODE == MODE_RESET) {
+        for (int i = gt; i < d.state_words; i += GS) st[i] = 0u;
+    } else {
+        const uint32_t* sin = a.state_in + (size_t)e * d.state_words;
+        for (int i = gt; i < d.state_words; i += GS) st[i] = sin[i];
+    }
+    if (gt == 0) {
+        misc[0] = 0;
+        mbar_init(bar, 1);
+    }
+    group_sync<GS>(gid);
+
+    int pidx;
+    if (MODE == MODE_RESET) pidx = a.prob_idx[e];
+    else pidx = (int)st_tail[ST_PIDX];
+    pidx = pidx < 0 ? 0 : (pidx >= a.P ? a.P - 1 : pidx);
+    if (gt == 0) {
+        mbar_expect_tx(bar, (uint32_t)d.rec_bytes);
+        tma_load_1d(rec, a.bank + (size_t)pidx * d.rec_bytes, (uint32_t)d.rec_bytes, bar);
+    }
+
+    // ---- new assignment while the record is in flight ----
+    if (MODE == MODE_RESET) {
+        threefry_assign<GS>(d, a.keys[2 * (size_t)e], a.keys[2 * (size_t)e + 1], st, gt);
+    } else if (MODE == MODE_STEP) {
+        apply_actions<GS>(d, a.actions, e, st, gt);
+    }
+    group_sync<GS>(gid);
+    mbar_wait(bar, 0);
+
+    eval_clauses<GS>(d, lits, st, satw, &misc[0], gt);
+    group_sync<GS>(gid);
+    int nunsat = misc[0];
+
+    int step_old = (MODE == MODE_RESET) ? 0 : (int)st_tail[ST_STEP];
+    if (MODE == MODE_STEP) {
+        const bool solved = nunsat == 0;                                  // env:257
+        const bool done = solved || (step_old + 1 >= d.max_steps);        // env:258-259
+        // pre-reset outputs stored in the Transition (learner:467-478)
+        if (a.reward)
+            for (int i = gt; i < d.A; i += GS) a.reward[(size_t)e * d.A + i] = solved ? 1.0f : 0.0f;   // env:193
+        if (a.done)
+            for (int i = gt; i < a.done_cols; i += GS) a.done[(size_t)e * a.done_cols + i] = done ? 1 : 0;
+        if (gt == 0) {
+            if (a.solved) a.solved[e] = solved ? 1 : 0;
+            if (a.num_unsat) a.num_unsat[e] = nunsat;
+            if (a.episode_step) a.episode_step[e] = step_old + 1;        // env:281
+        }
+        if (done && a.auto_reset) {
+            // learner:425-464: swap in a fresh episode on a newly drawn formula (group-uniform branch)
+            group_sync<GS>(gid);   // everyone is done reading the old record / misc
+            pidx = a.prob_idx[e];
+            pidx = pidx < 0 ? 0 : (pidx >= a.P ? a.P - 1 : pidx);
+            if (gt == 0) {
+                misc[0] = 0;
+                fence_proxy_async();
+                mbar_expect_tx(bar, (uint32_t)d.rec_bytes);
+                tma_load_1d(rec, a.bank + (size_t)pidx * d.rec_bytes, (uint32_t)d.rec_bytes, bar);
+            }
+            for (int i = gt; i < d.aw; i += GS) st[i] = 0u;
+            group_sync<GS>(gid);
+            threefry_assign<GS>(d, a.keys[2 * (size_t)e], a.keys[2 * (size_t)e + 1], st, gt);
+            group_sync<GS>(gid);
+            mbar_wait(bar, 1);
+            eval_clauses<GS>(d, lits, st, satw, &misc[0], gt);
+            group_sync<GS>(gid);
+            nunsat = misc[0];
+            if (gt == 0) {
+                st_tail[ST_STEP] = 0u;
+                st_tail[ST_PIDX] = (uint32_t)pidx;
+                st_tail[ST_NUNSAT] = (uint32_t)nunsat;
+                st_tail[ST_FLAGS] = 0u;
+            }
+        } else if (gt == 0) {
+            st_tail[ST_STEP] = (uint32_t)(step_old + 1);                 // env:269
+            st_tail[ST_NUNSAT] = (uint32_t)nunsat;
+            st_tail[ST_FLAGS] = done ? 1u : 0u;                          // env:270
+        }
+    } else if (MODE == MODE_RESET) {
+        if (gt == 0) {
+            st_tail[ST_STEP] = 0u;                                       // env:170
+            st_tail[ST_PIDX] = (uint32_t)pidx;
+            st_tail[ST_NUNSAT] = (uint32_t)nunsat;
+            st_tail[ST_FLAGS] = 0u;                                      // env:171
+        }
+    }
+    if (MODE != MODE_OBS) {
+        group_sync<GS>(gid);
+        uint32_t* sout = a.state_out + (size_t)e * d.state_words;
+        for (int i = gt; i < d.state_words; i += GS) sout[i] = st[i];
+    }
+    if (a.obs) emit_obs<GS>(d, e, st, satw, X, smx, mflat, a.obs, gid, gt);
+}
+
+template <int GS>
+static cudaError_t launch_env_gs(const msat_plan* plan, EnvMode mode, const EnvArgs& a, cudaStream_t s) {
+    const int groups = kCtaThreads / GS;
+    const int grid = (a.B + groups - 1) / groups;
+    if (grid == 0) return cudaSuccess;
+    const void* fn = nullptr;
+    switch (mode) {
+        case MODE_RESET: fn = (const void*)env_kernel<GS, MODE_RESET>; break;
+        case MODE_STEP: fn = (const void*)env_kernel<GS, MODE_STEP>; break;
+        default: fn = (const void*)env_kernel<GS, MODE_OBS>; break;
+    }
+    if (plan->smem_bytes > 48 * 1024) {
+        cudaError_t err = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, plan->smem_bytes);
+        if (err != cudaSuccess) return err;
+    }
+    Dims d = plan->d;
+    EnvArgs args = a;
+    void* params[] = {&d, &args};
+    return cudaLaunchKernel(fn, dim3(grid), dim3(kCtaThreads), params, (size_t)plan->smem_bytes, s);
+}
+
+cudaError_t launch_env(const msat_plan* plan, EnvMode mode, const EnvArgs& a, cudaStream_t s) {
+    switch (plan->group_threads) {
+        case 32: return launch_env_gs<32>(plan, mode, a, s);
+        case 64: return launch_env_gs<64>(plan, mode, a, s);
+        case 128: return launch_env_gs<128>(plan, mode, a, s);
+        default: return launch_env_gs<256>(plan, mode, a, s);
+    }
+}
+
+cudaError_t launch_compile_bank(const msat_plan* plan, const int32_t* clauses, int P, uint8_t* bank, cudaStream_t s) {
+    if (P == 0) return cudaSuccess;
+    if (plan->compile_smem_bytes > 48 * 1024) {
+        cudaError_t err = cudaFuncSetAttribute((const void*)compile_bank_kernel,
+                                               cudaFuncAttributeMaxDynamicSharedMemorySize, plan->compile_smem_bytes);
+        if (err != cudaSuccess) return err;
+    }
+    compile_bank_kernel<<<P, 256, plan->compile_smem_bytes, s>>>(plan->d, clauses, bank);
+    return cudaGetLastError();
+}
+
+// =====================================================================================
+// K_export: reference-shaped SATState leaves (env:13-24) from packed state + bank.  Off the hot
+// path (API fidelity, parity tests); one 128-thread CTA per env, global-memory reads only.
+// =====================================================================================
+__global__ void __launch_bounds__(128) export_kernel(const Dims d, const ExportArgs a) {
+    const int e = blockIdx.x, tid = threadIdx.x, nt = blockDim.x;
+    const uint32_t* st = a.state + (size_t)e * d.state_words;
+    const uint32_t* tail = st + d.aw;
+    int pidx = (int)tail[ST_PIDX];
+    pidx = pidx < 0 ? 0 : (pidx >= a.P ? a.P - 1 : pidx);
+    const uint8_t* rec = a.bank + (size_t)pidx * d.rec_bytes;
+    const uint16_t* lits = reinterpret_cast<const uint16_t*>(rec);
+    const uint32_t* mflat = reinterpret_cast<const uint32_t*>(rec + d.lits_bytes);
+    if (a.assign)
+        for (int v = tid; v < d.n; v += nt) a.assign[(size_t)e * d.n + v] = (st[v >> 5] >> (v & 31)) & 1u;
+    if (a.sat)
+        for (int c = tid; c < d.m; c += nt) {
+            bool sat = false;
+            for (int j = 0; j < d.k; ++j) {
+                const uint32_t code = lits[c * d.k + j];
+                if (code != LIT_PAD) {
+                    const uint32_t v = code >> 1;
+                    sat |= (((st[v >> 5] >> (v & 31)) ^ code) & 1u) != 0u;
+                }
+            }
+            a.sat[(size_t)e * d.m + c] = sat ? 1 : 0;
+        }
+    if (tid == 0) {
+        if (a.num_unsat) a.num_unsat[e] = (int)tail[ST_NUNSAT];
+        if (a.step) a.step[e] = (int)tail[ST_STEP];
+        if (a.pidx) a.pidx[e] = pidx;
+    }
+    if (a.done)
+        for (int i = tid; i < d.A; i += nt) a.done[(size_t)e * d.A + i] = (uint8_t)(tail[ST_FLAGS] & 1u);
+    if (a.clauses || a.l2a)
+        for (int i = tid; i < d.m * d.k; i += nt) {
+            const uint32_t code = lits[i];
+            const int v = (code == LIT_PAD) ? -1 : (int)(code >> 1);
+            if (a.clauses) a.clauses[(size_t)e * d.m * d.k + i] = v < 0 ? 0 : ((code & 1u) ? -(v + 1) : (v + 1));
+            // env:160: index -1 wraps to the last variable
+            if (a.l2a) a.l2a[(size_t)e * d.m * d.k + i] = var_to_agent(d, v < 0 ? d.n - 1 : v);
+        }
+    if (a.acm)
+        for (int i = tid; i < d.A * d.m; i += nt) {
+            const int ag = i / d.m, c = i - ag * d.m;
+            const int j = ag * d.D + d.n + c;
+            a.acm[(size_t)e * d.A * d.m + i] = ((mflat[j >> 5] >> (j & 31)) & 1u) ? 1 : -1;
+        }
+    if (a.anm)
+        for (int i = tid; i < d.A * d.n; i += nt) {
+            const int ag = i / d.n, v = i - ag * d.n;
+            const int j = ag * d.D + d.n + d.m + v;
+            a.anm[(size_t)e * d.A * d.n + i] = ((mflat[j >> 5] >> (j & 31)) & 1u) ? 1 : -1;
+        }
+}
+
+cudaError_t launch_export(const msat_plan* plan, const ExportArgs& a, cudaStream_t s) {
+    if (a.B == 0) return cudaSuccess;
+    export_kernel<<<a.B, 128, 0, s>>>(plan->d, a);
+    return cudaGetLastError();
+}
+
+}  // namespace msat

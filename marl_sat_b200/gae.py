@@ -1,0 +1,65 @@
+"""MAPPO advantage path on device: GAE / return scan and global advantage normalisation.
+
+Mirrors ``_calculate_gae`` and the normalisation that follows it in the reference learner
+(``/root/reference/src/learners/mappo_gnn_sat_learner.py:504-532``).  With ``torch.distributed``
+initialised, the three normalisation statistics (count, sum, sum of squares; float64) are
+all-reduced so the result equals the single-device global mean/std over all ``T x B_global``
+elements -- the only collective on the advantage path.
+"""
+from __future__ import annotations
+
+from typing import Optional, Tuple
+
+import torch
+
+from . import _lib
+from .env import _ptr, _stream_ptr
+
+
+def calculate_gae(reward: torch.Tensor, done: torch.Tensor, value: torch.Tensor, last_val: torch.Tensor,
+                  gamma: float, gae_lambda: float) -> Tuple[torch.Tensor, torch.Tensor]:
+    """reward f32 ``[T,B,A]`` (agent 0 is read, learner:514) or ``[T,B]``; done bool/uint8 ``[T,B]``;
+    value f32 ``[T,B]``; last_val f32 ``[B]`` -> ``(advantages, targets)`` f32 ``[T,B]``
+    (``targets = advantages + value`` with un-normalised advantages, learner:526)."""
+    lib = _lib.load()
+    if not reward.is_cuda:
+        raise RuntimeError("calculate_gae needs CUDA tensors: there is no CPU fallback")
+    T, B = value.shape
+    if reward.dtype != torch.float32 or value.dtype != torch.float32 or last_val.dtype != torch.float32:
+        raise TypeError("reward/value/last_val must be float32")
+    if done.dtype == torch.bool:
+        done = done.view(torch.uint8)
+    done = done.contiguous()
+    value = value.contiguous()
+    last_val = last_val.contiguous()
+    if reward.dim() == 3:
+        rs_t, rs_b = reward.stride(0), reward.stride(1)
+    else:
+        rs_t, rs_b = reward.stride(0), reward.stride(1)
+    adv = torch.empty((T, B), dtype=torch.float32, device=value.device)
+    tgt = torch.empty((T, B), dtype=torch.float32, device=value.device)
+    _lib.check(lib.msat_gae(_ptr(reward), rs_t, rs_b, _ptr(done), _ptr(value), _ptr(last_val), float(gamma),
+                            float(gae_lambda), _ptr(adv), _ptr(tgt), T, B, _stream_ptr(value.device)), "msat_gae")
+    return adv, tgt
+
+
+def advantage_stats(adv: torch.Tensor, stats: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Accumulate ``(count, sum, sum of squares)`` of ``adv`` into a float64[3] device tensor."""
+    lib = _lib.load()
+    if stats is None:
+        stats = torch.zeros(3, dtype=torch.float64, device=adv.device)
+    _lib.check(lib.msat_adv_stats(_ptr(adv), adv.numel(), _ptr(stats), _stream_ptr(adv.device)), "msat_adv_stats")
+    return stats
+
+
+def normalize_advantages(adv: torch.Tensor, group=None) -> torch.Tensor:
+    """In place ``adv = (adv - mean) / (std + 1e-8)`` with the global population std (learner:530-532)."""
+    lib = _lib.load()
+    adv = adv if adv.is_contiguous() else adv.contiguous()
+    stats = advantage_stats(adv)
+    if torch.distributed.is_available() and torch.distributed.is_initialized() and \
+            torch.distributed.get_world_size(group) > 1:
+        torch.distributed.all_reduce(stats, op=torch.distributed.ReduceOp.SUM, group=group)
+    _lib.check(lib.msat_adv_normalize(_ptr(adv), adv.numel(), _ptr(stats), _stream_ptr(adv.device)),
+               "msat_adv_normalize")
+    return adv

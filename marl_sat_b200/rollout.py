@@ -1,0 +1,169 @@
+"""Rollout-side host logic: the per-step RNG chain, fused auto-reset stepping and the rollout buffer.
+
+Mirrors the env half of ``_env_step`` in the reference learner
+(``/root/reference/src/learners/mappo_gnn_sat_learner.py:383-480``, cited as learner:LINE) and the
+initial reset of the runner (``src/runners/mappo_runner.py:289-295``, runner:LINE):
+
+    rng, act_key  = split(rng)                      learner:397   (policy sampling key)
+    rng, step_key = split(rng)                      learner:416   (unused by SATEnv)
+    step all envs                                   learner:418
+    rng, prob_key, reset_key = split(rng, 3)        learner:426
+    new_problem_indices = randint(prob_key, B, P)   learner:430
+    reset_keys = split(reset_key, B)                learner:434
+    reset finished envs on their new formula        learner:435-464  (the reference resets *every*
+                                                    env and selects with where(done); the kernel
+                                                    resets only finished envs -- same result)
+
+Environments shard across ranks as contiguous blocks of the global batch with no data-path
+collective; the per-env keys are derived from *global* env indices so that any sharding yields the
+values of the single-device run.
+"""
+from __future__ import annotations
+
+from typing import Dict, Optional
+
+import torch
+
+from . import _lib
+from .env import FormulaBank, SATEnv, SATState, _ptr, _stream_ptr, as_u32_tensor
+
+
+def shard_range(num_envs_global: int, world_size: int, rank: int):
+    """Contiguous block ``[offset, offset + count)`` of the global env batch owned by ``rank``."""
+    base, rem = divmod(num_envs_global, world_size)
+    count = base + (1 if rank < rem else 0)
+    offset = rank * base + min(rank, rem)
+    return offset, count
+
+
+class RolloutKeys:
+    """Device-resident ``rng`` of the rollout carry and the per-step chain derived from it."""
+
+    def __init__(self, key, device: torch.device):
+        self.device = device
+        self._lib = _lib.load()
+        self.chain = torch.zeros(10, dtype=torch.int32, device=device)   # rng', act, step, prob, reset
+        self.chain[:2] = as_u32_tensor(key, device).reshape(2)
+
+    @property
+    def rng(self) -> torch.Tensor:
+        return self.chain[0:2]
+
+    @property
+    def act_key(self) -> torch.Tensor:
+        return self.chain[2:4]
+
+    @property
+    def step_key(self) -> torch.Tensor:
+        return self.chain[4:6]
+
+    @property
+    def prob_key(self) -> torch.Tensor:
+        return self.chain[6:8]
+
+    @property
+    def reset_key(self) -> torch.Tensor:
+        return self.chain[8:10]
+
+    def advance(self) -> None:
+        """One rollout step of the chain (learner:397,416,426), in place, enqueue only."""
+        _lib.check(self._lib.msat_rng_chain(_ptr(self.chain), _ptr(self.chain), _stream_ptr(self.device)),
+                   "msat_rng_chain")
+
+
+def derive_env_keys(prob_key: Optional[torch.Tensor], reset_key: Optional[torch.Tensor], num_envs_global: int,
+                    env_offset: int, num_envs_local: int, num_problems: int,
+                    problem_idx: Optional[torch.Tensor], reset_keys: Optional[torch.Tensor]) -> None:
+    """``randint(prob_key, (Bg,), 0, P)`` and ``split(reset_key, Bg)`` restricted to a shard."""
+    lib = _lib.load()
+    dev = (problem_idx if problem_idx is not None else reset_keys).device
+    _lib.check(lib.msat_env_keys(_ptr(prob_key), _ptr(reset_key), num_envs_global, env_offset, num_envs_local,
+                                 num_problems, _ptr(problem_idx), _ptr(reset_keys), _stream_ptr(dev)),
+               "msat_env_keys")
+
+
+class VecSATEnv:
+    """B parallel SATEnv episodes with the reference's auto-reset and RNG chain fused on device.
+
+    One instance per process/GPU; ``world_size``/``rank`` select the shard of the global batch.
+    All per-step work is enqueue-only on the current stream (no host sync, graph-capturable).
+    """
+
+    def __init__(self, env: SATEnv, problems: FormulaBank | torch.Tensor, num_envs: int, key,
+                 world_size: int = 1, rank: int = 0, emit_obs: bool = True):
+        self.env = env
+        dev = env._require_cuda()
+        self.bank = problems if isinstance(problems, FormulaBank) else env.make_bank(problems)
+        self.num_envs_global = int(num_envs)
+        self.env_offset, self.num_envs = shard_range(self.num_envs_global, world_size, rank)
+        self.keys = RolloutKeys(key, dev)
+        d = self.bank.plan.dims
+        B = self.num_envs
+        self.state = torch.empty((B, d.state_words), dtype=torch.int32, device=dev)
+        self.new_problem_idx = torch.empty((B,), dtype=torch.int32, device=dev)
+        self.reset_keys = torch.empty((B, 2), dtype=torch.int32, device=dev)
+        self.out = env.alloc_step_outputs(B, d, want_obs=emit_obs)
+        self._split_tmp = torch.empty(4, dtype=torch.int32, device=dev)
+
+    # runner:289-295 -- key,_rng = split(key); idx = randint(_rng,...); reset_keys = split(_rng, B)
+    def reset(self) -> Optional[torch.Tensor]:
+        lib, dev = self.env._lib, self.state.device
+        _lib.check(lib.msat_rng_split2(_ptr(self.keys.chain), _ptr(self._split_tmp), _stream_ptr(dev)), "msat_rng_split2")
+        self.keys.chain[0:2] = self._split_tmp[0:2]          # key
+        rng = self._split_tmp[2:4]                           # _rng, used for both draws (runner:291,294)
+        derive_env_keys(rng, rng, self.num_envs_global, self.env_offset, self.num_envs, self.bank.num_problems,
+                        self.new_problem_idx, self.reset_keys)
+        obs, _ = self.env.reset_from_bank(self.bank, self.new_problem_idx, self.reset_keys, state_out=self.state,
+                                          obs_out=self.out["obs"], want_obs=self.out["obs"] is not None)
+        return obs
+
+    def step(self, actions: torch.Tensor, out: Optional[Dict[str, torch.Tensor]] = None) -> Dict[str, torch.Tensor]:
+        """One rollout step (learner:397-464) for this shard.  ``actions`` int32 ``[B, A]`` (mode 0) or
+        ``[B, A, V]`` (mode 1) on the device.  Returns the output dict (obs of the state to continue
+        from; reward/done/info are the pre-reset values, learner:467-478)."""
+        out = self.out if out is None else out
+        self.keys.advance()
+        derive_env_keys(self.keys.prob_key, self.keys.reset_key, self.num_envs_global, self.env_offset, self.num_envs,
+                        self.bank.num_problems, self.new_problem_idx, self.reset_keys)
+        self.env.step_into(self.bank, self.state, self.state, actions, out, auto_reset=True,
+                           new_problem_idx=self.new_problem_idx, reset_keys=self.reset_keys)
+        return out
+
+    def sat_state(self) -> SATState:
+        return SATState(self.env, self.bank, self.state, True)
+
+
+class RolloutBuffer:
+    """``Transition`` storage (learner:358-369,467-478) for T steps of B envs, laid out ``[T, B, ...]`` so
+    the step kernel writes each step's slice in place (no stacking pass).  Observations are *not*
+    stored: the packed state (32 B/env at uf100-430) is, and ``SATEnv.get_obs`` regenerates the obs of
+    any stored step on demand (the reference stores 63 KB/env-step of obs)."""
+
+    def __init__(self, env: SATEnv, bank: FormulaBank, num_steps: int, num_envs: int):
+        dev = env._require_cuda()
+        d = bank.plan.dims
+        T, B, A = num_steps, num_envs, env.num_agents
+        act_shape = (T, B, A) if env.action_mode == 0 else (T, B, A, env.max_vars_per_agent)
+        self.env, self.bank, self.num_steps, self.num_envs = env, bank, T, B
+        self.state = torch.empty((T, B, d.state_words), dtype=torch.int32, device=dev)     # pre-step state
+        self.action = torch.empty(act_shape, dtype=torch.int32, device=dev)
+        self.reward = torch.empty((T, B, A), dtype=torch.float32, device=dev)
+        self.done = torch.empty((T, B, 1), dtype=torch.uint8, device=dev)                  # global_done only
+        self.solved = torch.empty((T, B), dtype=torch.uint8, device=dev)
+        self.num_unsatisfied = torch.empty((T, B), dtype=torch.int32, device=dev)
+        self.episode_step = torch.empty((T, B), dtype=torch.int32, device=dev)
+        self.value = torch.zeros((T, B), dtype=torch.float32, device=dev)
+        self.log_prob = torch.zeros(act_shape, dtype=torch.float32, device=dev)
+
+    def step_outputs(self, t: int, obs: Optional[torch.Tensor]) -> Dict[str, Optional[torch.Tensor]]:
+        return {"obs": obs, "reward": self.reward[t], "done": self.done[t], "solved": self.solved[t],
+                "num_unsatisfied": self.num_unsatisfied[t], "episode_step": self.episode_step[t]}
+
+    @property
+    def global_done(self) -> torch.Tensor:
+        """``Transition.global_done`` = done["__all__"] (learner:468), dense uint8 ``[T, B]``."""
+        return self.done[:, :, 0]
+
+    def local_obs(self, t: int) -> torch.Tensor:
+        """Observations the policy saw at step t (``Transition.local_obs``, learner:473)."""
+        return self.env.get_obs_array(SATState(self.env, self.bank, self.state[t], True))

@@ -1,0 +1,34 @@
+"""Synthetic CNF generators (host side, NumPy) shared by bench.py and the tests.
+
+``uniform_ksat`` draws SATLIB "uf"-style uniform random k-SAT: each clause has k distinct variables
+drawn uniformly from n, each negated with probability 1/2, no satisfiability filtering
+(SURVEY.md section 8d).  ``mixed_ksat`` draws clause widths uniformly in [kmin, kmax] and pads
+with literal 0 up to kmax (BASELINE config 5).
+"""
+from __future__ import annotations
+
+import numpy as np
+
+
+def uniform_ksat(num_formulas: int, n: int, m: int, k: int = 3, seed: int = 0) -> np.ndarray:
+    rng = np.random.default_rng(seed)
+    if k > n:
+        raise ValueError("k distinct variables need k <= n")
+    vars_ = rng.integers(0, n, size=(num_formulas, m, k), dtype=np.int64)
+    while True:   # re-draw rows with a repeated variable
+        s = np.sort(vars_, axis=2)
+        dup = (s[:, :, 1:] == s[:, :, :-1]).any(axis=2)
+        cnt = int(dup.sum())
+        if cnt == 0:
+            break
+        vars_[dup] = rng.integers(0, n, size=(cnt, k), dtype=np.int64)
+    sign = rng.integers(0, 2, size=vars_.shape, dtype=np.int64) * 2 - 1
+    return ((vars_ + 1) * sign).astype(np.int32)
+
+
+def mixed_ksat(num_formulas: int, n: int, m: int, kmin: int = 3, kmax: int = 7, seed: int = 0) -> np.ndarray:
+    rng = np.random.default_rng(seed)
+    full = uniform_ksat(num_formulas, n, m, kmax, seed=seed + 1)
+    width = rng.integers(kmin, kmax + 1, size=(num_formulas, m, 1))
+    keep = np.arange(kmax)[None, None, :] < width
+    return np.where(keep, full, 0).astype(np.int32)

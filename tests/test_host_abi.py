@@ -1,0 +1,121 @@
+"""CPU tests of the host layer: the C ABI library loads and exports every symbol declared in
+include/marl_sat_b200.h, plan/dims arithmetic, the drop-in SATEnv's constructor-time attributes,
+spaces, sharding arithmetic, and loud failure (no CPU fallback).  No kernel is launched here."""
+import ctypes as C
+import re
+from pathlib import Path
+
+import numpy as np
+import pytest
+import torch
+
+import marl_sat_b200 as M
+from marl_sat_b200 import _lib
+from oracle.sat_env import SATEnvOracle
+
+ROOT = Path(__file__).resolve().parent.parent
+
+
+def test_library_exports_every_declared_symbol():
+    header = (ROOT / "include" / "marl_sat_b200.h").read_text()
+    declared = set(re.findall(r"\b(msat_[a-z0-9_]+)\s*\(", header))
+    assert {"msat_step", "msat_reset", "msat_compile_bank", "msat_gae", "msat_env_keys"} <= declared
+    lib = C.CDLL(str(_lib.lib_path()))
+    missing = [s for s in sorted(declared) if not hasattr(lib, s)]
+    assert not missing, f"declared in the header but not exported: {missing}"
+    assert set(_lib.SIGNATURES) <= declared, sorted(set(_lib.SIGNATURES) - declared)
+    assert b"sm_100a" in _lib.load().msat_version()
+
+
+@pytest.mark.parametrize("n,m,vpa", [(20, 91, None), (35, 149, 7), (50, 218, None), (100, 430, None),
+                                     (250, 1065, None), (100, 430, 7), (7, 4, 4), (3, 5, None)])
+def test_constructor_matches_reference_grouping(n, m, vpa):
+    ref = SATEnvOracle(n, m, 10, vars_per_agent=vpa)
+    env = M.SATEnv(n, m, 10, vars_per_agent=vpa, verbose=False, device="cpu")
+    assert env.agents == ref.agents and env.agent_groups == ref.agent_groups
+    assert env.num_agents == ref.num_agents and env.max_vars_per_agent == ref.max_vars_per_agent
+    assert np.array_equal(env.agent_vars.numpy(), ref.agent_vars)
+    assert np.array_equal(env.action_mask.numpy(), ref.action_mask)
+    assert np.array_equal(env.variable_to_agent_idx.numpy(), ref.variable_to_agent_idx)
+    assert env.obs_dim == 2 * n + m and env.name == "SATEnv"
+    sp = env.action_space("agent_0")
+    assert sp.n == env.max_vars_per_agent + 1 and sp.dtype == torch.int32
+    ob = env.observation_space("agent_0")
+    assert ob.shape == (2 * n + m,) and ob.low == -1 and ob.high == 1 and ob.dtype == torch.float32
+    env1 = M.SATEnv(n, m, 10, vars_per_agent=vpa, action_mode=1, verbose=False, device="cpu")
+    assert env1.action_space("agent_0").num_categories.tolist() == [2] * env.max_vars_per_agent
+
+
+def test_constructor_prints_like_the_reference(capsys):
+    M.SATEnv(20, 91, 10, device="cpu")
+    out = capsys.readouterr().out
+    assert "Auto-distribution mode" in out and "Found ideal grouping: 5 agents, each with 4 vars." in out
+    M.SATEnv(35, 149, 10, vars_per_agent=7, device="cpu")
+    assert "User specified mode: aiming for 7 vars per agent." in capsys.readouterr().out
+
+
+def test_plan_dims():
+    env = M.SATEnv(100, 430, 512, verbose=False, device="cpu")
+    d = env._plan_for(3).dims
+    assert (d.n, d.m, d.k, d.A, d.V, d.D) == (100, 430, 3, 25, 4, 630)
+    assert d.rec_bytes % 128 == 0 and d.rec_bytes >= 430 * 3 * 2 + (25 * 630 + 7) // 8
+    assert d.state_words % 4 == 0 and d.state_words >= 4 + 4
+    assert d.group_threads in (32, 64, 128, 256) and 0 < d.smem_bytes <= 227 * 1024
+    lib = _lib.load()
+    h = C.c_void_p()
+    assert lib.msat_plan_create(C.byref(h), 0, 1, 3, 1, 0, 1, 0) == _lib.MSAT_EINVAL
+    assert lib.msat_plan_create(C.byref(h), 10, 5, 3, 11, 0, 1, 0) == _lib.MSAT_EINVAL       # A > n
+    assert lib.msat_plan_create(C.byref(h), 10, 5, 3, 2, 2, 1, 0) == _lib.MSAT_EINVAL        # bad mode
+    assert lib.msat_plan_create(C.byref(h), 10, 5, 3, 2, 0, 1, 48) == _lib.MSAT_EINVAL       # bad group size
+
+
+def test_argument_errors_enqueue_nothing():
+    lib = _lib.load()
+    env = M.SATEnv(20, 91, 8, verbose=False, device="cpu")
+    plan = env._plan_for(3).handle
+    assert lib.msat_reset(plan, None, 1, None, None, None, None, 4, None) == _lib.MSAT_EINVAL
+    assert lib.msat_step(plan, None, 1, None, None, None, 0, None, None, None, None, None, 0, None, None, None,
+                         4, None) == _lib.MSAT_EINVAL
+    assert lib.msat_env_keys(None, None, 8, 4, 8, 3, None, None, None) == _lib.MSAT_EINVAL   # shard exceeds batch
+    assert lib.msat_gae(None, 1, 1, None, None, None, 0.9, 0.9, None, None, 4, 4, None) == _lib.MSAT_EINVAL
+    buf = (C.c_char * 4096)()
+    addr = C.addressof(buf)
+    mis = addr + 4 if (addr + 4) % 128 else addr + 8
+    assert lib.msat_compile_bank(plan, addr, 1, mis, None) == _lib.MSAT_EALIGN
+
+
+def test_no_cpu_fallback():
+    env = M.SATEnv(20, 91, 8, verbose=False, device="cpu")
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        env.reset(np.ones((91, 3), np.int32), np.zeros(2, np.uint32))
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        M.calculate_gae(torch.zeros(2, 2), torch.zeros(2, 2, dtype=torch.bool), torch.zeros(2, 2), torch.zeros(2), 0.9, 0.9)
+
+
+def test_shard_range_partitions_the_batch():
+    for B in (1, 7, 16, 65536, 65537):
+        for world in (1, 2, 3, 4, 8):
+            spans = [M.shard_range(B, world, r) for r in range(world)]
+            assert spans[0][0] == 0 and sum(c for _, c in spans) == B
+            for (o0, c0), (o1, _) in zip(spans, spans[1:]):
+                assert o0 + c0 == o1
+
+
+def test_key_tensor_round_trip():
+    keys = np.array([[0, 1], [0xFFFFFFFF, 0x80000000], [123456789, 4000000000]], np.uint32)
+    t = M.env.as_u32_tensor(keys, torch.device("cpu"))
+    assert t.dtype == torch.int32 and np.array_equal(M.env.u32_to_numpy(t), keys)
+    t64 = M.env.as_u32_tensor(torch.from_numpy(keys.astype(np.int64)), torch.device("cpu"))
+    assert np.array_equal(M.env.u32_to_numpy(t64), keys)
+
+
+def test_config_reader_mirrors_runner_mapping(tmp_path):
+    from marl_sat_b200 import config
+    p = tmp_path / "cfg.yaml"
+    p.write_text("SEED: 42\nenvironment:\n  NUM_VARS: 35\n  NUM_CLAUSES: 149\n  MAX_STEPS: 512\n  VARS_PER_AGENT: 7\n"
+                 "  action_mode: 0\n  rewards:\n    R_CLAUSE: 0.0\n    R_SAT: 20.0\ntraining:\n  GAMMA: 0.995\n  NUM_ENVS: 128\n")
+    cfg = config.load_config(str(p))
+    flat = config.flatten(cfg)
+    assert flat["NUM_VARS"] == 35 and flat["NUM_ENVS"] == 128
+    env = config.make_env(cfg, verbose=False, device="cpu")
+    assert env.num_agents == 5 and env.max_steps == 512 and env.r_sat == 20.0 and env.gamma == 0.995
