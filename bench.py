@@ -1,0 +1,410 @@
+#!/usr/bin/env python
+"""Benchmark of the batched SATEnv hot path (BASELINE.json metric: SATEnv env-steps/s, uf100-430).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload NAME]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 \
+        --master-port P bench.py --gpus N --steps K --warmup W
+
+One "step" = one rollout step of every environment: the device RNG chain (learner:397-434), the
+per-env problem-index / reset-key derivation and the fused flip + clause evaluation + reward / done /
+info + auto-reset + observation kernel.  The global batch (65,536 envs for the headline workload) is
+sharded across the N ranks in contiguous blocks with no collective on the step path; `value` is
+global env-steps/s from CUDA-event time, max over ranks.  Rank 0 prints ONE JSON line.
+
+`--impl reference` times the CPU restatement of the reference algorithm (oracle/, NumPy, one process
+per host core) on a bounded sample of the same workload: the reference's own JAX build cannot run here
+(no JAX in the image), see DESIGN.md section 6.
+"""
+from __future__ import annotations
+
+import argparse
+import importlib.util
+import json
+import os
+import sys
+import threading
+import time
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent
+if str(ROOT) not in sys.path:
+    sys.path.insert(0, str(ROOT))
+
+METRIC = "SATEnv env-steps/s, uf100-430, 1/2/4/8 B200; achieved HBM GB/s vs peak"
+UNIT = "env-steps/s"
+
+# name -> shape (BASELINE.json configs / SURVEY.md Appendix C)
+WORKLOADS = {
+    "uf20-91": dict(n=20, m=91, k=3, vpa=None, envs=16, kind="uniform"),
+    "uf50-218": dict(n=50, m=218, k=3, vpa=None, envs=4096, kind="uniform"),
+    "uf100-430": dict(n=100, m=430, k=3, vpa=None, envs=65536, kind="uniform"),      # headline
+    "uf250-1065": dict(n=250, m=1065, k=3, vpa=None, envs=16384, kind="uniform"),
+    "mixed-k3-7": dict(n=100, m=430, k=7, vpa=7, envs=32768, kind="mixed"),
+}
+MAX_STEPS = 512          # configs/MAPPO_CONFIG.yaml:14
+SEED = 42                # configs/MAPPO_CONFIG.yaml:6
+ACTION_CYCLE = 64        # pre-generated action batches, cycled
+
+
+def _load_synth():
+    spec = importlib.util.spec_from_file_location("_msat_synth", ROOT / "marl_sat_b200" / "synth.py")
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+def make_formulas(w, count, seed):
+    synth = _load_synth()
+    if w["kind"] == "mixed":
+        return synth.mixed_ksat(count, w["n"], w["m"], 3, w["k"], seed)
+    return synth.uniform_ksat(count, w["n"], w["m"], w["k"], seed)
+
+
+def algorithmic_bytes_per_env_step(n, m, k, A):
+    """obs write + literals read + packed state r/w + actions + rewards +
+    dones + info + reset key / problem index."""
+    D = 2 * n + m
+    return (4 * A * D + 4 * m * k + 2 * (4 * ((n + 31) // 32) + 4 * ((m + 31) // 32) + 8)
+            + 4 * A + 4 * A + (A + 1) + 9 + 12)
+
+
+# ----------------------------------------------------------------------------------------------
+# CPU restatement arm (oracle/): one process per core, each stepping its own shard of envs
+# ----------------------------------------------------------------------------------------------
+def _cpu_worker(args):
+    wname, envs, steps, warmup, seed = args
+    import numpy as np
+    from oracle import rollout as orollout
+    from oracle import threefry as otf
+    from oracle.sat_env import SATEnvOracle
+    w = WORKLOADS[wname]
+    problems = make_formulas(w, envs, seed)
+    env = SATEnvOracle(w["n"], w["m"], MAX_STEPS, vars_per_agent=w["vpa"])
+    key, idx, rk = orollout.initial_reset_inputs(otf.prng_key(seed), envs, envs)
+    _, st = env.reset(problems[idx], rk)
+    rng = np.random.default_rng(seed)
+    t0 = 0.0
+    for i in range(warmup + steps):
+        if i == warmup:
+            t0 = time.perf_counter()
+        acts = rng.integers(0, env.max_vars_per_agent + 1, size=(envs, env.num_agents)).astype(np.int32)
+        ks = orollout.rollout_keys(key, envs, envs)
+        key = ks["rng"]
+        _, st, _, _, _ = orollout.env_step_with_autoreset(env, st, acts, problems, ks["new_problem_indices"],
+                                                          ks["reset_keys"])
+    return time.perf_counter() - t0
+
+
+def run_cpu_restatement(wname, envs_per_worker, steps, warmup):
+    import multiprocessing as mp
+    cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    ctx = mp.get_context("spawn")       # safe next to an initialised CUDA context; workers import NumPy only
+    jobs = [(wname, envs_per_worker, steps, warmup, 1000 + i) for i in range(cores)]
+    with ctx.Pool(cores) as pool:
+        times = pool.map(_cpu_worker, jobs)
+    t = max(times)
+    total = envs_per_worker * cores * steps
+    return {"value": total / t, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": f"{wname}: {cores} processes x {envs_per_worker} envs x {steps} steps (+{warmup} warm-up) of the "
+                      f"NumPy restatement (step all, reset all, select by done; learner:418-464), "
+                      f"{t:.2f} s"}, t
+
+
+def main_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    wname = args.workload
+    w = WORKLOADS[wname]
+    envs_per_worker = args.cpu_envs_per_core
+    base, t = run_cpu_restatement(wname, envs_per_worker, args.steps, args.warmup)
+    cores = base["cores"]
+    line = {
+        "impl": "reference", "metric": METRIC, "value": base["value"], "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t / max(1, args.steps),
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "int32", "data": "synthetic",
+        "config": {"workload": f"{wname} (n={w['n']}, m={w['m']}, k={w['k']}), bounded sample of "
+                               f"{envs_per_worker * cores} envs per step on {cores} host cores",
+                   "max_steps": MAX_STEPS, "auto_reset": True},
+        "cpu_baseline": base,
+        "e2e": {"value": base["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "note": "CPU restatement of the reference algorithm (oracle/, NumPy); the reference's JAX build is not "
+                "installable in this image (no jax wheel, no network)",
+    }
+    print(json.dumps(line))
+    return 0
+
+
+# ----------------------------------------------------------------------------------------------
+# clocks (NVML sampled in a thread during the timed region)
+# ----------------------------------------------------------------------------------------------
+class ClockSampler:
+    REASONS = {0x4: "sw_power_cap", 0x8: "hw_slowdown", 0x20: "sw_thermal_slowdown", 0x40: "hw_thermal_slowdown",
+               0x80: "hw_power_brake_slowdown", 0x2: "applications_clocks_setting", 0x10: "sync_boost"}
+
+    def __init__(self, torch_device_index):
+        self.samples = []
+        self._stop = threading.Event()
+        self._thread = None
+        self.max_mhz = None
+        self.ok = False
+        try:
+            import pynvml
+            import torch
+            pynvml.nvmlInit()
+            uuid = str(torch.cuda.get_device_properties(torch_device_index).uuid)
+            if not uuid.startswith("GPU-"):
+                uuid = "GPU-" + uuid
+            try:
+                self.h = pynvml.nvmlDeviceGetHandleByUUID(uuid.encode())
+            except Exception:
+                self.h = pynvml.nvmlDeviceGetHandleByIndex(torch_device_index)
+            self.nv = pynvml
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+            self.ok = True
+        except Exception as e:          # pragma: no cover
+            self.err = repr(e)
+
+    def _loop(self):
+        nv = self.nv
+        while not self._stop.is_set():
+            try:
+                mhz = nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)
+                try:
+                    reasons = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:
+                    reasons = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                self.samples.append((time.perf_counter(), mhz, reasons))
+            except Exception:
+                pass
+            time.sleep(0.004)
+
+    def start(self):
+        if self.ok:
+            self._thread = threading.Thread(target=self._loop, daemon=True)
+            self._thread.start()
+
+    def stop(self):
+        if self._thread:
+            self._stop.set()
+            self._thread.join(timeout=2)
+
+    def summary(self, t0, t1):
+        if not self.ok:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "error": getattr(self, "err", "nvml unavailable")}
+        inside = [s for s in self.samples if t0 <= s[0] <= t1]
+        window = "timed region"
+        if len(inside) < 3:
+            inside, window = self.samples, "whole loaded period (timed region too short to sample)"
+        mhz = sorted(s[1] for s in inside)
+        bits = 0
+        for s in inside:
+            bits |= s[2]
+        return {"sm_mhz": mhz[len(mhz) // 2] if mhz else None, "sm_max_mhz": self.max_mhz,
+                "reasons": [name for bit, name in self.REASONS.items() if bits & bit],
+                "samples": len(inside), "window": window}
+
+
+# ----------------------------------------------------------------------------------------------
+# CUDA arm
+# ----------------------------------------------------------------------------------------------
+def main_ours(args):
+    import torch
+    import torch.distributed as dist
+
+    import marl_sat_b200 as M
+    from oracle import threefry as otf   # PRNGKey(seed) constructor only ([0, seed]); no compute
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (no CPU fallback); use --impl reference for the CPU arm")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    if args.gpus != world and rank == 0:
+        print(f"[bench] note: --gpus {args.gpus} but WORLD_SIZE={world}; using {world}", file=sys.stderr)
+
+    wname = args.workload
+    w = WORKLOADS[wname]
+    Bg = args.envs or w["envs"]
+    if args.scaling == "weak":
+        Bg *= world
+    env = M.SATEnv(w["n"], w["m"], MAX_STEPS, vars_per_agent=w["vpa"], verbose=False, device=dev,
+                   group_threads=args.group_threads)
+    P = args.problems or Bg
+    problems = torch.from_numpy(make_formulas(w, P, 20261018 + 2))
+    bank = env.make_bank(problems)
+    del problems
+    vec = M.VecSATEnv(env, bank, Bg, otf.prng_key(SEED), world_size=world, rank=rank)
+    B = vec.num_envs
+    A, V = env.num_agents, env.max_vars_per_agent
+    gen = torch.Generator(device=dev).manual_seed(1234 + rank)
+    actions = torch.randint(0, V + 1, (ACTION_CYCLE, B, A), generator=gen, device=dev, dtype=torch.int32)
+    vec.reset()
+    torch.cuda.synchronize()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+
+    K, W = args.steps, args.warmup
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+
+    # ---- device-resident throughput: `value` -------------------------------------------------
+    for i in range(W):
+        vec.step(actions[i % ACTION_CYCLE])
+    torch.cuda.synchronize()
+    barrier()
+    torch.cuda.synchronize()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t_wall0 = time.perf_counter()
+    ev0.record()
+    for i in range(K):
+        vec.step(actions[(W + i) % ACTION_CYCLE])
+    ev1.record()
+    torch.cuda.synchronize()
+    t_wall1 = time.perf_counter()
+    barrier()
+    ms = ev0.elapsed_time(ev1)
+    launches = 3 * K                       # rng_chain + env_keys + env_kernel<STEP> per step
+
+    # ---- dominant kernel alone (roofline): K launches of msat_step, same arguments --------------
+    kev0, kev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    for i in range(3):
+        env.step_into(bank, vec.state, vec.state, actions[i], vec.out, auto_reset=True,
+                      new_problem_idx=vec.new_problem_idx, reset_keys=vec.reset_keys)
+    torch.cuda.synchronize()
+    kev0.record()
+    for i in range(K):
+        env.step_into(bank, vec.state, vec.state, actions[i % ACTION_CYCLE], vec.out, auto_reset=True,
+                      new_problem_idx=vec.new_problem_idx, reset_keys=vec.reset_keys)
+    kev1.record()
+    torch.cuda.synchronize()
+    kernel_ms = kev0.elapsed_time(kev1) / K
+
+    # ---- end to end through the host-buffer entry point: `e2e` -------------------------------------
+    host = vec.alloc_host_io()
+    host_actions = [actions[i].cpu().pin_memory() for i in range(4)]
+    Ke = max(1, min(K, args.e2e_steps))
+    for i in range(2):
+        host["actions"].copy_(host_actions[i % 4])
+        vec.step_host(host)
+    torch.cuda.synchronize()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(Ke):
+        host["actions"] = host_actions[i % 4]
+        vec.step_host(host)
+        _ = int(host["solved"][0])          # the host reads the step's result
+    e1.record()
+    torch.cuda.synchronize()
+    barrier()
+    e2e_ms = e0.elapsed_time(e1)
+    h2d = B * A * 4
+    d2h = B * (4 * A + (A + 1) + 1 + 4 + 4)
+
+    # optional: also bring the observations to the host (PCIe-bound; reported separately)
+    e2e_obs = None
+    if args.e2e_obs_steps > 0:
+        obs_host = torch.empty(vec.out["obs"].shape, dtype=torch.int32, pin_memory=True)
+        o0, o1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        vec.step_host(host)
+        obs_host.copy_(vec.out["obs"], non_blocking=True)
+        torch.cuda.synchronize()
+        barrier()
+        o0.record()
+        for i in range(args.e2e_obs_steps):
+            vec.step_host(host)
+            obs_host.copy_(vec.out["obs"], non_blocking=True)
+            torch.cuda.synchronize()
+        o1.record()
+        torch.cuda.synchronize()
+        e2e_obs = (o0.elapsed_time(o1), obs_host.numel() * 4)
+        del obs_host
+    sampler.stop()
+
+    # ---- reduce over ranks (max time) ------------------------------------------------------------------
+    t = torch.tensor([ms, kernel_ms, e2e_ms, e2e_obs[0] if e2e_obs else 0.0], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms, kernel_ms_max, e2e_ms, e2e_obs_ms = [float(x) for x in t.tolist()]
+
+    if rank == 0:
+        alg = algorithmic_bytes_per_env_step(w["n"], w["m"], w["k"], A)
+        peaks_file = ROOT / "MEASURED_PEAKS.json"
+        if peaks_file.exists():
+            peak, peak_src = float(json.loads(peaks_file.read_text())["hbm_gbs"]), "of measured (MEASURED_PEAKS.json hbm_gbs)"
+        else:
+            peak, peak_src = 6650.0, "of fallback (B200_PROFILING.md 6.65 TB/s)"
+        achieved = alg * B / (kernel_ms * 1e-3) / 1e9          # rank 0's own kernel time
+        traffic = None
+        tf = ROOT / "profiles" / "traffic.json"
+        if tf.exists():
+            try:
+                rec = json.loads(tf.read_text()).get(f"{wname}:{B}")
+                traffic = rec["dram_bytes_per_launch"] if rec else None
+            except Exception:
+                traffic = None
+        value = Bg * K / (ms * 1e-3)
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": ms / K, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
+            "dtype": "u32", "data": "synthetic",
+            "config": {"workload": f"{wname}: uniform random {w['k']}-SAT n={w['n']} m={w['m']}, {A} agents x {V} vars, "
+                                   f"obs_dim {env.obs_dim}, {Bg} envs sharded over {world} GPU(s) ({B} on rank 0), "
+                                   f"{P} distinct formulas, max_steps {MAX_STEPS}, auto-reset on, action_mode 0",
+                       "envs_global": Bg, "envs_per_gpu": B, "problems": P,
+                       "group_threads": bank.plan.dims.group_threads,
+                       "l2": f"no flush: each step writes {B * A * env.obs_dim * 4 / 1e6:.0f} MB of observations per GPU "
+                             f"(> 126 MB L2) and cycles {ACTION_CYCLE} action batches"},
+            "clocks": sampler.summary(t_wall0, t_wall1),
+            "e2e": {"value": Bg * Ke / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d * world,
+                    "d2h_bytes_per_step": d2h * world, "steps": Ke,
+                    "what": "VecSATEnv.step_host -> msat_step_host: pinned host actions in; reward, done, solved, "
+                            "num_unsatisfied, episode_step out to pinned host memory and read by the host every step; "
+                            "observations stay in HBM for the policy"},
+            "gpu_launches": launches,
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": traffic, "peak_source": peak_src, "kernel": "msat::env_kernel<GS, MODE_STEP>",
+                         "kernel_ms": kernel_ms, "algorithmic_bytes_per_env_step": alg, "envs_per_launch": B},
+        }
+        if e2e_obs:
+            line["e2e_obs_to_host"] = {"value": Bg * args.e2e_obs_steps / (e2e_obs_ms * 1e-3), "unit": UNIT,
+                                       "d2h_bytes_per_step": (d2h + e2e_obs[1]) * world, "steps": args.e2e_obs_steps,
+                                       "what": "as e2e, plus the int32 observations copied to pinned host memory"}
+        if world == 1 and not args.no_cpu_baseline:
+            line["cpu_baseline"], _ = run_cpu_restatement(wname, args.cpu_envs_per_core, 5, 1)
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+def parse_args(argv=None):
+    ap = argparse.ArgumentParser(description=__doc__, formatter_class=argparse.RawDescriptionHelpFormatter)
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
+    ap.add_argument("--workload", choices=sorted(WORKLOADS), default="uf100-430")
+    ap.add_argument("--envs", type=int, default=0, help="global env count (default: the workload's)")
+    ap.add_argument("--problems", type=int, default=0, help="distinct formulas in the bank (default: = envs)")
+    ap.add_argument("--scaling", choices=["strong", "weak"], default="strong",
+                    help="strong: the global batch is fixed and sharded (BASELINE configs[2]); weak: per-GPU batch fixed")
+    ap.add_argument("--group-threads", type=int, default=0)
+    ap.add_argument("--e2e-steps", type=int, default=50)
+    ap.add_argument("--e2e-obs-steps", type=int, default=2)
+    ap.add_argument("--cpu-envs-per-core", type=int, default=128)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args(argv)
+
+
+if __name__ == "__main__":
+    a = parse_args()
+    sys.exit(main_reference(a) if a.impl == "reference" else main_ours(a))

@@ -129,6 +129,40 @@ class VecSATEnv:
                            new_problem_idx=self.new_problem_idx, reset_keys=self.reset_keys)
         return out
 
+    def alloc_host_io(self) -> Dict[str, torch.Tensor]:
+        """Pinned host buffers for ``step_host``: the action batch in, reward/done/info out."""
+        env, B = self.env, self.num_envs
+        act_shape = (B, env.num_agents) if env.action_mode == 0 else (B, env.num_agents, env.max_vars_per_agent)
+        pin = dict(pin_memory=True)
+        return {"actions": torch.zeros(act_shape, dtype=torch.int32, **pin),
+                "reward": torch.empty((B, env.num_agents), dtype=torch.float32, **pin),
+                "done": torch.empty((B, env.num_agents + 1), dtype=torch.uint8, **pin),
+                "solved": torch.empty((B,), dtype=torch.uint8, **pin),
+                "num_unsatisfied": torch.empty((B,), dtype=torch.int32, **pin),
+                "episode_step": torch.empty((B,), dtype=torch.int32, **pin)}
+
+    def step_host(self, host: Dict[str, torch.Tensor], actions_dev: Optional[torch.Tensor] = None) -> Dict[str, torch.Tensor]:
+        """End-to-end step for a host-side caller (``msat_step_host``): host actions are copied to the
+        device, the rollout step runs, reward/done/info are copied back and the stream is synchronised.
+        Observations stay in HBM (``self.out['obs']``) where the policy consumes them."""
+        out, dev = self.out, self.state.device
+        if actions_dev is None:
+            if not hasattr(self, "_actions_dev"):
+                self._actions_dev = torch.empty(host["actions"].shape, dtype=torch.int32, device=dev)
+            actions_dev = self._actions_dev
+        self.keys.advance()
+        derive_env_keys(self.keys.prob_key, self.keys.reset_key, self.num_envs_global, self.env_offset, self.num_envs,
+                        self.bank.num_problems, self.new_problem_idx, self.reset_keys)
+        done = out["done"]
+        _lib.check(self.env._lib.msat_step_host(
+            self.bank.plan.handle, _ptr(self.bank.data), self.bank.num_problems, _ptr(self.state),
+            _ptr(host["actions"]), _ptr(actions_dev), 1, _ptr(self.new_problem_idx), _ptr(self.reset_keys),
+            _ptr(out["obs"]), _ptr(out["reward"]), _ptr(done), int(done.shape[-1]), _ptr(out["solved"]),
+            _ptr(out["num_unsatisfied"]), _ptr(out["episode_step"]),
+            _ptr(host["reward"]), _ptr(host["done"]), _ptr(host["solved"]), _ptr(host["num_unsatisfied"]),
+            _ptr(host["episode_step"]), self.num_envs, _stream_ptr(dev)), "msat_step_host")
+        return host
+
     def sat_state(self) -> SATState:
         return SATState(self.env, self.bank, self.state, True)
 

@@ -14,16 +14,19 @@ def uniform_ksat(num_formulas: int, n: int, m: int, k: int = 3, seed: int = 0) -
     rng = np.random.default_rng(seed)
     if k > n:
         raise ValueError("k distinct variables need k <= n")
-    vars_ = rng.integers(0, n, size=(num_formulas, m, k), dtype=np.int64)
+    vars_ = rng.integers(0, n, size=(num_formulas, m, k), dtype=np.int16 if n < 2 ** 15 else np.int32)
     while True:   # re-draw rows with a repeated variable
-        s = np.sort(vars_, axis=2)
-        dup = (s[:, :, 1:] == s[:, :, :-1]).any(axis=2)
+        dup = np.zeros(vars_.shape[:2], dtype=bool)
+        for i in range(k):
+            for j in range(i + 1, k):
+                dup |= vars_[:, :, i] == vars_[:, :, j]
         cnt = int(dup.sum())
         if cnt == 0:
             break
-        vars_[dup] = rng.integers(0, n, size=(cnt, k), dtype=np.int64)
-    sign = rng.integers(0, 2, size=vars_.shape, dtype=np.int64) * 2 - 1
-    return ((vars_ + 1) * sign).astype(np.int32)
+        vars_[dup] = rng.integers(0, n, size=(cnt, k), dtype=vars_.dtype)
+    neg = rng.integers(0, 2, size=vars_.shape, dtype=np.int8).astype(bool)
+    lits = vars_.astype(np.int32) + 1
+    return np.where(neg, -lits, lits)
 
 
 def mixed_ksat(num_formulas: int, n: int, m: int, kmin: int = 3, kmax: int = 7, seed: int = 0) -> np.ndarray:
