@@ -118,6 +118,21 @@ int msat_step(const msat_plan* plan, const void* bank, int32_t num_problems,
               int32_t* num_unsatisfied, int32_t* episode_step,
               int32_t num_envs, void* stream);
 
+/* One whole rollout step of the learner's `_env_step` env half (learner:397-464) in ONE launch:
+ * msat_rng_chain + msat_env_keys + msat_step(auto_reset=1) fused.  The kernel advances the rollout
+ * rng (rng_in uint32[2] -> chain_out uint32[10] = {rng', act_key, step_key, prob_key, reset_key};
+ * the two buffers must not overlap) and every env that finishes derives its own new problem index
+ * and reset key from the advanced chain with its GLOBAL env index env_offset + b out of
+ * num_envs_global, so any sharding of the batch reproduces the single-device values.  Other
+ * arguments as msat_step. */
+int msat_rollout_step(const msat_plan* plan, const void* bank, int32_t num_problems,
+                      const uint32_t* state_in, uint32_t* state_out, const int32_t* actions,
+                      const uint32_t* rng_in, uint32_t* chain_out,
+                      int32_t num_envs_global, int32_t env_offset,
+                      int32_t* obs, float* reward, uint8_t* done, int32_t done_cols, uint8_t* solved,
+                      int32_t* num_unsatisfied, int32_t* episode_step,
+                      int32_t num_envs, void* stream);
+
 /* Replaces `SATEnv.get_obs(state)` (env:345-398): obs int32[B,A,D] from a state. */
 int msat_get_obs(const msat_plan* plan, const void* bank, int32_t num_problems,
                  const uint32_t* state, int32_t* obs, int32_t num_envs, void* stream);

@@ -70,6 +70,46 @@ __host__ __device__ __forceinline__ void split2(uint32_t k0, uint32_t k1, uint32
     a[0] = p0; a[1] = q0; b[0] = p1; b[1] = q1;
 }
 
+// One rollout step of the key chain (learner:397,416,426):
+//   rng,act = split(rng); rng,step = split(rng); rng,prob,reset = split(rng,3)
+// out[10] = {rng', act_key, step_key, prob_key, reset_key}.
+__host__ __device__ __forceinline__ void rng_chain_compute(uint32_t r0, uint32_t r1, uint32_t out[10]) {
+    uint32_t a[2], b[2];
+    split2(r0, r1, a, b);                       // rng <- a, act_key <- b
+    out[2] = b[0]; out[3] = b[1];
+    r0 = a[0]; r1 = a[1];
+    split2(r0, r1, a, b);                       // rng <- a, step_key <- b
+    out[4] = b[0]; out[5] = b[1];
+    r0 = a[0]; r1 = a[1];
+    // split(rng, 3) = threefry_2x32(rng, arange(6)).reshape(3, 2): blocks (0,3),(1,4),(2,5)
+    uint32_t x0 = 0u, x1 = 3u, y0 = 1u, y1 = 4u, z0 = 2u, z1 = 5u;
+    threefry2x32(r0, r1, x0, x1);
+    threefry2x32(r0, r1, y0, y1);
+    threefry2x32(r0, r1, z0, z1);
+    out[0] = x0; out[1] = y0;                   // rng'
+    out[6] = z0; out[7] = x1;                   // prob_key
+    out[8] = y1; out[9] = z1;                   // reset_key
+}
+
+// problem index and reset key of global env g out of Bg (learner:430,434):
+//   randint(prob_key, (Bg,), 0, P)[g]  and  split(reset_key, Bg)[g]
+__host__ __device__ __forceinline__ uint32_t env_problem_index(uint32_t pk0, uint32_t pk1, uint32_t Bg, uint32_t g,
+                                                               uint32_t P) {
+    uint32_t k1[2], k2[2];
+    split2(pk0, pk1, k1, k2);
+    const uint32_t hi = bits32_at(k1[0], k1[1], Bg, g);
+    const uint32_t lo = bits32_at(k2[0], k2[1], Bg, g);
+    const uint32_t span = P > 0u ? P : 1u;
+    uint32_t mult = 65536u % span;
+    mult = (mult * mult) % span;
+    return ((hi % span) * mult + (lo % span)) % span;
+}
+__host__ __device__ __forceinline__ void env_reset_key(uint32_t rk0, uint32_t rk1, uint32_t Bg, uint32_t g,
+                                                       uint32_t key[2]) {
+    key[0] = bits32_at(rk0, rk1, 2u * Bg, 2u * g);
+    key[1] = bits32_at(rk0, rk1, 2u * Bg, 2u * g + 1u);
+}
+
 // ---- bit-stream helpers ------------------------------------------------------
 // 32 bits starting at bit `pos` of a clean little-endian bit array of `nwords` words
 // (bits past the logical end are zero; reads outside the array return zero).  pos may be negative.

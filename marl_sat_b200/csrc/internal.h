@@ -28,7 +28,7 @@ __host__ __device__ inline GroupLayout group_layout(const Dims& d) {
     o = (o + 7) & ~7;
     L.smx = o;  o += 8 * (d.fw + 2);              // {mask word, value word} per 32 observation ints
     L.bar = o;  o += 8;                           // mbarrier
-    L.misc = o; o += 8;                           // [0] = #unsatisfied accumulator
+    L.misc = o; o += 16;                          // [0] #unsatisfied accumulator, [1] new problem idx, [2..3] reset key
     L.total = (o + 127) & ~127;
     return L;
 }
@@ -41,6 +41,9 @@ struct EnvArgs {
     const int32_t* actions;
     const int32_t* prob_idx;
     const uint32_t* keys;
+    const uint32_t* rng_in;     // fused key derivation (msat_rollout_step): rollout rng before this step
+    uint32_t* chain_out;        // ... and the advanced chain {rng', act, step, prob, reset}
+    uint32_t Bg, env_off;       // global batch size and this shard's first global env index
     int auto_reset;
     int32_t* obs;
     float* reward;

@@ -7,21 +7,9 @@ namespace msat {
 // rng,act = split(rng); rng,step = split(rng); rng,prob,reset = split(rng,3)   (learner:397,416,426)
 __global__ void rng_chain_kernel(const uint32_t* __restrict__ rng_in, uint32_t* __restrict__ out) {
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
-    uint32_t r[2] = {rng_in[0], rng_in[1]}, a[2], b[2];
-    split2(r[0], r[1], a, b);                 // rng <- a, act_key <- b
-    const uint32_t act0 = b[0], act1 = b[1];
-    r[0] = a[0]; r[1] = a[1];
-    split2(r[0], r[1], a, b);                 // rng <- a, step_key <- b
-    const uint32_t st0 = b[0], st1 = b[1];
-    r[0] = a[0]; r[1] = a[1];
-    // split(rng, 3): threefry_2x32(rng, arange(6)).reshape(3, 2)
-    uint32_t w[6];
-    for (uint32_t i = 0; i < 6; ++i) w[i] = bits32_at(r[0], r[1], 6u, i);
-    out[0] = w[0]; out[1] = w[1];             // rng'
-    out[2] = act0; out[3] = act1;
-    out[4] = st0;  out[5] = st1;
-    out[6] = w[2]; out[7] = w[3];             // prob_key
-    out[8] = w[4]; out[9] = w[5];             // reset_key
+    uint32_t out10[10];
+    rng_chain_compute(rng_in[0], rng_in[1], out10);
+    for (int i = 0; i < 10; ++i) out[i] = out10[i];
 }
 
 __global__ void rng_split2_kernel(const uint32_t* __restrict__ key_in, uint32_t* __restrict__ out) {
@@ -40,20 +28,12 @@ __global__ void __launch_bounds__(256) env_keys_kernel(const uint32_t* __restric
     const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= Bl) return;
     const uint32_t g = off + b;
-    if (idx) {
-        uint32_t k1[2], k2[2];
-        split2(prob_key[0], prob_key[1], k1, k2);
-        const uint32_t hi = bits32_at(k1[0], k1[1], Bg, g);
-        const uint32_t lo = bits32_at(k2[0], k2[1], Bg, g);
-        const uint32_t span = P > 0u ? P : 1u;
-        uint32_t mult = 65536u % span;
-        mult = (mult * mult) % span;
-        const uint32_t o = ((hi % span) * mult + (lo % span)) % span;
-        idx[b] = (int32_t)o;
-    }
+    if (idx) idx[b] = (int32_t)env_problem_index(prob_key[0], prob_key[1], Bg, g, P);
     if (keys) {
-        keys[2 * b + 0] = bits32_at(reset_key[0], reset_key[1], 2u * Bg, 2u * g);
-        keys[2 * b + 1] = bits32_at(reset_key[0], reset_key[1], 2u * Bg, 2u * g + 1u);
+        uint32_t k[2];
+        env_reset_key(reset_key[0], reset_key[1], Bg, g, k);
+        keys[2 * b + 0] = k[0];
+        keys[2 * b + 1] = k[1];
     }
 }
 

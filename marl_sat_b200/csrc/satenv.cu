@@ -288,6 +288,12 @@ __global__ void __launch_bounds__(kCtaThreads) env_kernel(const Dims d, const En
 
     int step_old = (MODE == MODE_RESET) ? 0 : (int)st_tail[ST_STEP];
     if (MODE == MODE_STEP) {
+        if (a.rng_in && blockIdx.x == 0 && threadIdx.x == 0) {
+            // advance the rollout rng once per step (learner:397,416,426); chain_out never aliases rng_in
+            uint32_t c[10];
+            rng_chain_compute(a.rng_in[0], a.rng_in[1], c);
+            for (int i = 0; i < 10; ++i) a.chain_out[i] = c[i];
+        }
         const bool solved = nunsat == 0;                                  // env:257
         const bool done = solved || (step_old + 1 >= d.max_steps);        // env:258-259
         // pre-reset outputs stored in the Transition (learner:467-478)
@@ -303,7 +309,26 @@ __global__ void __launch_bounds__(kCtaThreads) env_kernel(const Dims d, const En
         if (done && a.auto_reset) {
             // learner:425-464: swap in a fresh episode on a newly drawn formula (group-uniform branch)
             group_sync<GS>(gid);   // everyone is done reading the old record / misc
-            pidx = a.prob_idx[e];
+            uint32_t rk0, rk1;
+            if (a.rng_in) {
+                // fused key derivation (learner:426-434) from the rollout rng, global env index
+                if (gt == 0) {
+                    uint32_t c[10], k[2];
+                    rng_chain_compute(a.rng_in[0], a.rng_in[1], c);
+                    misc[1] = (int)env_problem_index(c[6], c[7], a.Bg, a.env_off + (uint32_t)e, (uint32_t)a.P);
+                    env_reset_key(c[8], c[9], a.Bg, a.env_off + (uint32_t)e, k);
+                    misc[2] = (int)k[0];
+                    misc[3] = (int)k[1];
+                }
+                group_sync<GS>(gid);
+                pidx = misc[1];
+                rk0 = (uint32_t)misc[2];
+                rk1 = (uint32_t)misc[3];
+            } else {
+                pidx = a.prob_idx[e];
+                rk0 = a.keys[2 * (size_t)e];
+                rk1 = a.keys[2 * (size_t)e + 1];
+            }
             pidx = pidx < 0 ? 0 : (pidx >= a.P ? a.P - 1 : pidx);
             if (gt == 0) {
                 misc[0] = 0;
@@ -313,7 +338,7 @@ __global__ void __launch_bounds__(kCtaThreads) env_kernel(const Dims d, const En
             }
             for (int i = gt; i < d.aw; i += GS) st[i] = 0u;
             group_sync<GS>(gid);
-            threefry_assign<GS>(d, a.keys[2 * (size_t)e], a.keys[2 * (size_t)e + 1], st, gt);
+            threefry_assign<GS>(d, rk0, rk1, st, gt);
             group_sync<GS>(gid);
             mbar_wait(bar, 1);
             eval_clauses<GS>(d, lits, st, satw, &misc[0], gt);

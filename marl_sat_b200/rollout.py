@@ -37,13 +37,29 @@ def shard_range(num_envs_global: int, world_size: int, rank: int):
 
 
 class RolloutKeys:
-    """Device-resident ``rng`` of the rollout carry and the per-step chain derived from it."""
+    """Device-resident ``rng`` of the rollout carry and the per-step chain derived from it.
+
+    Two 10-word buffers are used alternately so that the fused step kernel can read the current rng
+    from one while it writes the advanced chain ``{rng', act, step, prob, reset}`` into the other."""
 
     def __init__(self, key, device: torch.device):
         self.device = device
         self._lib = _lib.load()
-        self.chain = torch.zeros(10, dtype=torch.int32, device=device)   # rng', act, step, prob, reset
-        self.chain[:2] = as_u32_tensor(key, device).reshape(2)
+        self._bufs = torch.zeros((2, 10), dtype=torch.int32, device=device)
+        self._cur = 0
+        self._bufs[0, :2] = as_u32_tensor(key, device).reshape(2)
+
+    @property
+    def chain(self) -> torch.Tensor:
+        """uint32[10] (as int32 bits): rng, act_key, step_key, prob_key, reset_key of the latest step."""
+        return self._bufs[self._cur]
+
+    @property
+    def next_chain(self) -> torch.Tensor:
+        return self._bufs[1 - self._cur]
+
+    def flip(self) -> None:
+        self._cur = 1 - self._cur
 
     @property
     def rng(self) -> torch.Tensor:
@@ -66,9 +82,10 @@ class RolloutKeys:
         return self.chain[8:10]
 
     def advance(self) -> None:
-        """One rollout step of the chain (learner:397,416,426), in place, enqueue only."""
-        _lib.check(self._lib.msat_rng_chain(_ptr(self.chain), _ptr(self.chain), _stream_ptr(self.device)),
+        """One rollout step of the chain (learner:397,416,426), enqueue only."""
+        _lib.check(self._lib.msat_rng_chain(_ptr(self.chain), _ptr(self.next_chain), _stream_ptr(self.device)),
                    "msat_rng_chain")
+        self.flip()
 
 
 def derive_env_keys(prob_key: Optional[torch.Tensor], reset_key: Optional[torch.Tensor], num_envs_global: int,
@@ -90,8 +107,9 @@ class VecSATEnv:
     """
 
     def __init__(self, env: SATEnv, problems: FormulaBank | torch.Tensor, num_envs: int, key,
-                 world_size: int = 1, rank: int = 0, emit_obs: bool = True):
+                 world_size: int = 1, rank: int = 0, emit_obs: bool = True, fused_keys: bool = True):
         self.env = env
+        self.fused_keys = fused_keys
         dev = env._require_cuda()
         self.bank = problems if isinstance(problems, FormulaBank) else env.make_bank(problems)
         self.num_envs_global = int(num_envs)
@@ -109,7 +127,7 @@ class VecSATEnv:
     def reset(self) -> Optional[torch.Tensor]:
         lib, dev = self.env._lib, self.state.device
         _lib.check(lib.msat_rng_split2(_ptr(self.keys.chain), _ptr(self._split_tmp), _stream_ptr(dev)), "msat_rng_split2")
-        self.keys.chain[0:2] = self._split_tmp[0:2]          # key
+        self.keys.chain[0:2].copy_(self._split_tmp[0:2])     # key
         rng = self._split_tmp[2:4]                           # _rng, used for both draws (runner:291,294)
         derive_env_keys(rng, rng, self.num_envs_global, self.env_offset, self.num_envs, self.bank.num_problems,
                         self.new_problem_idx, self.reset_keys)
@@ -122,6 +140,18 @@ class VecSATEnv:
         ``[B, A, V]`` (mode 1) on the device.  Returns the output dict (obs of the state to continue
         from; reward/done/info are the pre-reset values, learner:467-478)."""
         out = self.out if out is None else out
+        if self.fused_keys:
+            # one launch: rng chain + per-env key derivation + step + auto-reset (msat_rollout_step)
+            done = out.get("done")
+            _lib.check(self.env._lib.msat_rollout_step(
+                self.bank.plan.handle, _ptr(self.bank.data), self.bank.num_problems, _ptr(self.state),
+                _ptr(self.state), _ptr(actions), _ptr(self.keys.chain), _ptr(self.keys.next_chain),
+                self.num_envs_global, self.env_offset, _ptr(out.get("obs")), _ptr(out.get("reward")), _ptr(done),
+                int(done.shape[-1]) if done is not None else 0, _ptr(out.get("solved")),
+                _ptr(out.get("num_unsatisfied")), _ptr(out.get("episode_step")), self.num_envs,
+                _stream_ptr(self.state.device)), "msat_rollout_step")
+            self.keys.flip()
+            return out
         self.keys.advance()
         derive_env_keys(self.keys.prob_key, self.keys.reset_key, self.num_envs_global, self.env_offset, self.num_envs,
                         self.bank.num_problems, self.new_problem_idx, self.reset_keys)

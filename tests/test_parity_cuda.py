@@ -156,16 +156,17 @@ def test_negative_and_out_of_range_actions_follow_jax_indexing():
     assert_state_equal(st_c, st_r)
 
 
+@pytest.mark.parametrize("fused", [False, True], ids=["separate-key-kernels", "fused-keys"])
 @pytest.mark.parametrize("n,m,vpa,B,P,max_steps", [(20, 91, None, 64, 10, 3), (35, 149, 7, 33, 5, 2),
                                                    (100, 430, None, 48, 48, 2)])
-def test_rollout_autoreset_and_rng_chain(n, m, vpa, B, P, max_steps):
+def test_rollout_autoreset_and_rng_chain(n, m, vpa, B, P, max_steps, fused):
     """VecSATEnv (fused auto-reset + device RNG chain) against the oracle restatement of learner:383-480."""
     M = _msat()
     problems = _formulas("uniform", P, n, m, 3, seed=11)
     ref = SATEnvOracle(n, m, max_steps, vars_per_agent=vpa)
     env = M.SATEnv(n, m, max_steps, vars_per_agent=vpa, verbose=False)
     key0 = otf.prng_key(42)
-    vec = M.VecSATEnv(env, torch.from_numpy(problems), B, key0)
+    vec = M.VecSATEnv(env, torch.from_numpy(problems), B, key0, fused_keys=fused)
     obs_c = vec.reset()
     key, idx0, rk0 = orollout.initial_reset_inputs(key0, B, P)
     obs_r, st_r = ref.reset(problems[idx0], rk0)
@@ -185,8 +186,9 @@ def test_rollout_autoreset_and_rng_chain(n, m, vpa, B, P, max_steps):
         out = vec.step(torch.from_numpy(acts).cuda())
         assert np.array_equal(M.env.u32_to_numpy(vec.keys.chain),
                               np.concatenate([ks["rng"], ks["act_key"], ks["step_key"], ks["prob_key"], ks["reset_key"]]))
-        assert np.array_equal(to_np(vec.new_problem_idx), ks["new_problem_indices"])
-        assert np.array_equal(M.env.u32_to_numpy(vec.reset_keys), ks["reset_keys"])
+        if not fused:
+            assert np.array_equal(to_np(vec.new_problem_idx), ks["new_problem_indices"])
+            assert np.array_equal(M.env.u32_to_numpy(vec.reset_keys), ks["reset_keys"])
         assert np.array_equal(to_np(out["obs"]), fo), f"step {t} obs"
         assert np.array_equal(to_np(out["reward"]), rew_r)
         assert np.array_equal(to_np(out["done"]).astype(bool), np.repeat(done_r[:, None], ref.num_agents + 1, 1))
