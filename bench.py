@@ -177,7 +177,7 @@ class ClockSampler:
                 self.samples.append((time.perf_counter(), mhz, reasons))
             except Exception:
                 pass
-            time.sleep(0.004)
+            time.sleep(0.010)
 
     def start(self):
         if self.ok:
@@ -232,16 +232,18 @@ def main_ours(args):
     Bg = args.envs or w["envs"]
     if args.scaling == "weak":
         Bg *= world
+    # debugging aid: run the shard that rank R of an N-rank job would own, alone on this GPU
+    shard_world, shard_rank = (args.emulate_shard if args.emulate_shard else (world, rank))
     env = M.SATEnv(w["n"], w["m"], MAX_STEPS, vars_per_agent=w["vpa"], verbose=False, device=dev,
                    group_threads=args.group_threads)
     P = args.problems or Bg
     problems = torch.from_numpy(make_formulas(w, P, 20261018 + 2))
     bank = env.make_bank(problems)
     del problems
-    vec = M.VecSATEnv(env, bank, Bg, otf.prng_key(SEED), world_size=world, rank=rank)
+    vec = M.VecSATEnv(env, bank, Bg, otf.prng_key(SEED), world_size=shard_world, rank=shard_rank)
     B = vec.num_envs
     A, V = env.num_agents, env.max_vars_per_agent
-    gen = torch.Generator(device=dev).manual_seed(1234 + rank)
+    gen = torch.Generator(device=dev).manual_seed(1234 + shard_rank)
     actions = torch.randint(0, V + 1, (ACTION_CYCLE, B, A), generator=gen, device=dev, dtype=torch.int32)
     vec.reset()
     torch.cuda.synchronize()
@@ -251,8 +253,13 @@ def main_ours(args):
             dist.barrier()
 
     K, W = args.steps, args.warmup
-    sampler = ClockSampler(local_rank)
-    sampler.start()
+    # pinned host buffers of the e2e leg are allocated up front (no allocation between timed regions)
+    host = vec.alloc_host_io()
+    host_actions = [actions[i].cpu().pin_memory() for i in range(4)]
+    torch.cuda.synchronize()
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    if sampler:
+        sampler.start()
 
     # ---- device-resident throughput: `value` -------------------------------------------------
     for i in range(W):
@@ -268,9 +275,11 @@ def main_ours(args):
     ev1.record()
     torch.cuda.synchronize()
     t_wall1 = time.perf_counter()
+    if sampler:
+        sampler.stop()
     barrier()
     ms = ev0.elapsed_time(ev1)
-    launches = 3 * K                       # rng_chain + env_keys + env_kernel<STEP> per step
+    launches = K                           # one fused msat_rollout_step launch per step
 
     # ---- dominant kernel alone (roofline): K launches of msat_step, same arguments --------------
     kev0, kev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -287,8 +296,6 @@ def main_ours(args):
     kernel_ms = kev0.elapsed_time(kev1) / K
 
     # ---- end to end through the host-buffer entry point: `e2e` -------------------------------------
-    host = vec.alloc_host_io()
-    host_actions = [actions[i].cpu().pin_memory() for i in range(4)]
     Ke = max(1, min(K, args.e2e_steps))
     for i in range(2):
         host["actions"].copy_(host_actions[i % 4])
@@ -310,7 +317,7 @@ def main_ours(args):
 
     # optional: also bring the observations to the host (PCIe-bound; reported separately)
     e2e_obs = None
-    if args.e2e_obs_steps > 0:
+    if args.e2e_obs_steps > 0 and world == 1:
         obs_host = torch.empty(vec.out["obs"].shape, dtype=torch.int32, pin_memory=True)
         o0, o1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         vec.step_host(host)
@@ -326,7 +333,6 @@ def main_ours(args):
         torch.cuda.synchronize()
         e2e_obs = (o0.elapsed_time(o1), obs_host.numel() * 4)
         del obs_host
-    sampler.stop()
 
     # ---- reduce over ranks (max time) ------------------------------------------------------------------
     t = torch.tensor([ms, kernel_ms, e2e_ms, e2e_obs[0] if e2e_obs else 0.0], dtype=torch.float64, device=dev)
@@ -402,9 +408,33 @@ def parse_args(argv=None):
     ap.add_argument("--e2e-obs-steps", type=int, default=2)
     ap.add_argument("--cpu-envs-per-core", type=int, default=128)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--emulate-shard", type=int, nargs=2, metavar=("WORLD", "RANK"), default=None,
+                    help="debug: single process, but own the env shard of RANK out of WORLD")
+    ap.add_argument("--watchdog", type=int, default=420,
+                    help="seconds after which all thread stacks are dumped to stderr and the process exits")
     return ap.parse_args(argv)
+
+
+def _guard_stdout():
+    """Keep the real stdout for the ONE JSON line and point fd 1 at stderr so that library chatter
+    (e.g. NCCL's version banner) cannot land in front of it."""
+    sys.stdout.flush()
+    real = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+    return real
 
 
 if __name__ == "__main__":
     a = parse_args()
+    if a.watchdog > 0:      # never hang the caller: dump every thread's stack and exit
+        import faulthandler
+        faulthandler.dump_traceback_later(a.watchdog, exit=True)
+    _json_out = _guard_stdout()
+    _print = print
+
+    def print(*args, **kw):  # noqa: A001  (the JSON line goes to the real stdout)
+        kw.setdefault("file", _json_out)
+        _print(*args, **kw)
+        kw["file"].flush()
+
     sys.exit(main_reference(a) if a.impl == "reference" else main_ours(a))
