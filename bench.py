@@ -334,6 +334,37 @@ def main_ours(args):
         e2e_obs = (o0.elapsed_time(o1), obs_host.numel() * 4)
         del obs_host
 
+    # ---- MAPPO advantage path on the same batch (learner:504-532): T x B GAE scan + normalisation -------
+    gae_info = None
+    if world == 1 and not args.no_gae:
+        T = args.gae_steps
+        gg = torch.Generator(device=dev).manual_seed(7)
+        g_reward = (torch.rand((T, B), generator=gg, device=dev) < 0.01).float()
+        g_done = (torch.rand((T, B), generator=gg, device=dev) < 0.005).to(torch.uint8)
+        g_value = torch.randn((T, B), generator=gg, device=dev)
+        g_last = torch.randn((B,), generator=gg, device=dev)
+        adv = None
+        for _ in range(3):
+            adv, tgt = M.calculate_gae(g_reward, g_done, g_value, g_last, 0.995, 0.95)
+        torch.cuda.synchronize()
+        g0, g1, g2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+        reps = 10
+        g0.record()
+        for _ in range(reps):
+            adv, tgt = M.calculate_gae(g_reward, g_done, g_value, g_last, 0.995, 0.95)
+        g1.record()
+        for _ in range(reps):
+            M.normalize_advantages(adv)
+        g2.record()
+        torch.cuda.synchronize()
+        scan_ms, norm_ms = g0.elapsed_time(g1) / reps, g1.elapsed_time(g2) / reps
+        gae_info = {"num_steps": T, "num_envs": B, "scan_ms": scan_ms, "normalize_ms": norm_ms,
+                    "scan_bytes_per_element": 17, "scan_gbs": 17.0 * T * B / (scan_ms * 1e-3) / 1e9,
+                    "normalize_bytes_per_element": 12, "normalize_gbs": 12.0 * T * B / (norm_ms * 1e-3) / 1e9,
+                    "note": "synthetic rollout, inputs resident in HBM; 17 B/element = reward 4 + done 1 + value 4 + "
+                            "adv 4 + target 4; normalisation = statistics pass (4 B read) + in-place map (8 B)"}
+        del g_reward, g_done, g_value, g_last, adv, tgt
+
     # ---- reduce over ranks (max time) ------------------------------------------------------------------
     t = torch.tensor([ms, kernel_ms, e2e_ms, e2e_obs[0] if e2e_obs else 0.0], dtype=torch.float64, device=dev)
     if world > 1:
@@ -383,6 +414,9 @@ def main_ours(args):
             line["e2e_obs_to_host"] = {"value": Bg * args.e2e_obs_steps / (e2e_obs_ms * 1e-3), "unit": UNIT,
                                        "d2h_bytes_per_step": (d2h + e2e_obs[1]) * world, "steps": args.e2e_obs_steps,
                                        "what": "as e2e, plus the int32 observations copied to pinned host memory"}
+        if gae_info:
+            gae_info["scan_frac_of_hbm_peak"] = gae_info["scan_gbs"] / peak
+            line["gae"] = gae_info
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"], _ = run_cpu_restatement(wname, args.cpu_envs_per_core, 5, 1)
         print(json.dumps(line))
@@ -408,6 +442,8 @@ def parse_args(argv=None):
     ap.add_argument("--e2e-obs-steps", type=int, default=2)
     ap.add_argument("--cpu-envs-per-core", type=int, default=128)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-gae", action="store_true")
+    ap.add_argument("--gae-steps", type=int, default=512, help="T of the GAE leg (configs/MAPPO_CONFIG.yaml NUM_STEPS)")
     ap.add_argument("--emulate-shard", type=int, nargs=2, metavar=("WORLD", "RANK"), default=None,
                     help="debug: single process, but own the env shard of RANK out of WORLD")
     ap.add_argument("--watchdog", type=int, default=420,

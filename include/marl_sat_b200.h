@@ -202,6 +202,36 @@ int msat_adv_stats(const float* adv, int64_t count, double* stats, void* stream)
 /* adv = (adv - mean) / (std + 1e-8), population std, from stats (learner:530-532). */
 int msat_adv_normalize(float* adv, int64_t count, const double* stats, void* stream);
 
+/* --- next-tier rows ----------------------------------------------- */
+
+/* Static part of the GNN input, once per formula (graph_constructor.py:93-114; learner:150-164):
+ * static_var_features float[P,n,3] = {positive degree / m, negative degree / m, 0}; optional dense
+ * occurrence-count matrices a_pos / a_neg float[P,n,m] (NULL = skip; duplicates accumulate). */
+int msat_gnn_static(const msat_plan* plan, const void* bank, int32_t num_problems,
+                    float* static_var_features, float* a_pos, float* a_neg, void* stream);
+
+/* Dynamic part of the GNN input, per env (learner:165-195): assignment int32[B,n] and
+ * clause_features float[B,m,3] = {is_sat, #true literals / 3.0, 1}.  Either may be NULL. */
+int msat_gnn_dynamic(const msat_plan* plan, const void* bank, int32_t num_problems,
+                     const uint32_t* state, int32_t num_envs,
+                     int32_t* assignment, float* clause_features, void* stream);
+
+/* Rollout metric sums (learner:661-686) over a [T,B] rollout: sums double[5] += {sum of team reward,
+ * #finished episodes, #solved at finish, sum of num_unsatisfied at finish, sum of episode_step of
+ * solved-at-finish}.  Not cleared by the call (zero it first; shards can be all-reduced).
+ * reward element (t,b) at reward[t*reward_stride_t + b*reward_stride_b]; the other arrays dense [T,B]. */
+int msat_rollout_metrics(const float* reward, int64_t reward_stride_t, int64_t reward_stride_b,
+                         const uint8_t* done, const uint8_t* solved, const int32_t* num_unsatisfied,
+                         const int32_t* episode_step, int32_t num_steps, int32_t num_envs,
+                         double* sums, void* stream);
+
+/* Bookkeeping of the greedy evaluation loop (runner:57-70) after evaluation step t (0-based): envs
+ * solved for the first time get ever_solved = 1, steps_to_solve = t+1 and solution int32[B,n] = their
+ * assignment.  Initialise ever_solved = 0, steps_to_solve = max_steps, solution = 0 before step 0. */
+int msat_eval_track(const msat_plan* plan, const uint32_t* state, const uint8_t* solved, int32_t t,
+                    int32_t num_envs, uint8_t* ever_solved, int32_t* steps_to_solve, int32_t* solution,
+                    void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -52,6 +52,10 @@ SIGNATURES = {
     "msat_gae": (C.c_int, [_p, _i64, _i64, _p, _p, _p, _f64, _f64, _p, _p, _i32, _i32, _p]),
     "msat_adv_stats": (C.c_int, [_p, _i64, _p, _p]),
     "msat_adv_normalize": (C.c_int, [_p, _i64, _p, _p]),
+    "msat_gnn_static": (C.c_int, [_p, _p, _i32, _p, _p, _p, _p]),
+    "msat_gnn_dynamic": (C.c_int, [_p, _p, _i32, _p, _i32, _p, _p, _p]),
+    "msat_rollout_metrics": (C.c_int, [_p, _i64, _i64, _p, _p, _p, _p, _i32, _i32, _p, _p]),
+    "msat_eval_track": (C.c_int, [_p, _p, _p, _i32, _i32, _p, _p, _p, _p]),
 }
 
 _lib = None

@@ -53,6 +53,7 @@ int msat_plan_create(msat_plan** out, int32_t n, int32_t m, int32_t k, int32_t A
     d.xw = (d.D + 31) / 32 + 1;
     d.fw = (d.AD + 31) / 32;
     d.agw = (A + 31) / 32;
+    d.inv_D = (uint32_t)(((1ULL << 32) + (uint64_t)d.D - 1) / (uint64_t)d.D);
     d.lits_bytes = (m * k * 2 + 15) & ~15;
     d.rec_bytes = (d.lits_bytes + 4 * (d.fw + 1) + 127) & ~127;
     d.state_words = (d.aw + 4 + 3) & ~3;
@@ -236,6 +237,38 @@ int msat_adv_stats(const float* adv, int64_t count, double* stats, void* stream)
 int msat_adv_normalize(float* adv, int64_t count, const double* stats, void* stream) {
     if (count < 0 || !stats || (count > 0 && !adv)) return MSAT_EINVAL;
     return cuda_rc(launch_adv_normalize(adv, count, stats, (cudaStream_t)stream));
+}
+
+int msat_gnn_static(const msat_plan* plan, const void* bank, int32_t P, float* static_var_features, float* a_pos,
+                    float* a_neg, void* stream) {
+    if (!plan || P < 0 || (P > 0 && !bank)) return MSAT_EINVAL;
+    if (2 * plan->d.n * (int)sizeof(int) > 48 * 1024) return MSAT_EUNSUPPORTED;
+    return cuda_rc(launch_gnn_static(plan, static_cast<const uint8_t*>(bank), P, static_var_features, a_pos, a_neg,
+                                     (cudaStream_t)stream));
+}
+
+int msat_gnn_dynamic(const msat_plan* plan, const void* bank, int32_t P, const uint32_t* state, int32_t B,
+                     int32_t* assignment, float* clause_features, void* stream) {
+    if (!plan || B < 0 || P <= 0 || (B > 0 && (!bank || !state))) return MSAT_EINVAL;
+    return cuda_rc(launch_gnn_dynamic(plan, static_cast<const uint8_t*>(bank), P, state, B, assignment,
+                                      clause_features, (cudaStream_t)stream));
+}
+
+int msat_rollout_metrics(const float* reward, int64_t rs_t, int64_t rs_b, const uint8_t* done, const uint8_t* solved,
+                         const int32_t* num_unsatisfied, const int32_t* episode_step, int32_t T, int32_t B,
+                         double* sums, void* stream) {
+    if (T < 0 || B < 0 || !sums) return MSAT_EINVAL;
+    if (T > 0 && B > 0 && (!reward || !done || !solved || !num_unsatisfied || !episode_step)) return MSAT_EINVAL;
+    return cuda_rc(launch_rollout_metrics(reward, rs_t, rs_b, done, solved, num_unsatisfied, episode_step, T, B, sums,
+                                          (cudaStream_t)stream));
+}
+
+int msat_eval_track(const msat_plan* plan, const uint32_t* state, const uint8_t* solved, int32_t t, int32_t B,
+                    uint8_t* ever_solved, int32_t* steps_to_solve, int32_t* solution, void* stream) {
+    if (!plan || B < 0 || t < 0) return MSAT_EINVAL;
+    if (B > 0 && (!state || !solved || !ever_solved || !steps_to_solve || !solution)) return MSAT_EINVAL;
+    return cuda_rc(launch_eval_track(plan, state, solved, t, B, ever_solved, steps_to_solve, solution,
+                                     (cudaStream_t)stream));
 }
 
 }  // extern "C"

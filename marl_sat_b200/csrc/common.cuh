@@ -15,6 +15,7 @@ struct Dims {
     int rec_bytes;        // bank record size (multiple of 128)
     int state_words;      // env-state record words (multiple of 4)
     int agw;              // words of an agent bit-set = ceil(A/32)
+    uint32_t inv_D;       // ceil(2^32 / D): j / D = umulhi(j, inv_D) (minus 1 when that overshoots)
 };
 
 // State record word offsets (after the aw assignment words).

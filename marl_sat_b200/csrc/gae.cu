@@ -1,55 +1,88 @@
 // MAPPO GAE / return scan and advantage normalisation (src/learners/mappo_gnn_sat_learner.py:504-532).
-// HBM-bound streaming kernels: one thread per env column, time steps walked in reverse with the next
-// chunk of loads issued before the current chunk's dependent chain is evaluated.
+// HBM-bound streaming kernels: lane = env column (coalesced), the time axis walked in reverse and, when
+// the batch alone cannot fill the GPU, split into segments that are scanned as affine maps and composed.
 #include "internal.h"
 
 namespace msat {
 
-constexpr int GAE_CHUNK = 8;
+constexpr int GAE_CHUNK = 8;      // loads in flight per array and thread in the segmented scan
+constexpr int GAE_CHUNK_1 = 16;   // ... and in the plain (S = 1) scan, which has fewer warps per SM
 
-// for t = T-1..0: nt = 1-done; delta = r + gamma*v_next*nt - v; gae = delta + (gamma*lambda)*nt*gae
-// (learner:515-516); adv[t] = gae; targets = adv + value (learner:526).  No FMA contraction so the
-// rounding sequence is the reference's mul/add sequence.
-__global__ void __launch_bounds__(64) gae_kernel(const float* __restrict__ reward, long long rs_t, long long rs_b,
-                                                 const uint8_t* __restrict__ done, const float* __restrict__ value,
-                                                 const float* __restrict__ last_val, float gamma, float gl,
-                                                 float* __restrict__ adv, float* __restrict__ targets, int T, int B) {
-    const int b = blockIdx.x * blockDim.x + threadIdx.x;
-    if (b >= B) return;
-    float gae = 0.0f;
-    float next_value = last_val[b];
-    float r[GAE_CHUNK], v[GAE_CHUNK], rn[GAE_CHUNK], vn[GAE_CHUNK];
-    uint8_t dn[GAE_CHUNK], dnn[GAE_CHUNK];
-
-    auto load = [&](int t_hi, float* rr, float* vv, uint8_t* dd) {
+// Reverse recurrence over one time segment [t0, t1) of one env column (learner:515-516):
+//   nt = 1-done; delta = r + gamma*v_next*nt - v; gae = delta + (gamma*lambda)*nt*gae.
+// No FMA contraction, so within a segment the rounding sequence is the reference's mul/add sequence.
+// WRITE = false: only the segment's affine map gae_out = bsum + aprod * gae_in is accumulated.
+template <bool WRITE, int CH>
+__device__ __forceinline__ void gae_segment(const float* __restrict__ reward, long long rs_t, long long rs_b,
+                                            const uint8_t* __restrict__ done, const float* __restrict__ value,
+                                            float gamma, float gl, float* __restrict__ adv,
+                                            float* __restrict__ targets, int B, int b, int t0, int t1,
+                                            float next_value, float& gae, float& aprod) {
+    for (int t_hi = t1 - 1; t_hi >= t0; t_hi -= CH) {
+        float r[CH], v[CH];
+        uint8_t dn[CH];
 #pragma unroll
-        for (int i = 0; i < GAE_CHUNK; ++i) {
+        for (int i = 0; i < CH; ++i) {          // all loads of the chunk first (memory-level parallelism)
             const int t = t_hi - i;
-            if (t >= 0) {
-                rr[i] = __ldcs(reward + (long long)t * rs_t + (long long)b * rs_b);
-                vv[i] = __ldcs(value + (size_t)t * B + b);
-                dd[i] = __ldcs(done + (size_t)t * B + b);
+            if (t >= t0) {
+                r[i] = __ldg(reward + (long long)t * rs_t + (long long)b * rs_b);
+                v[i] = __ldg(value + (size_t)t * B + b);
+                dn[i] = __ldg(done + (size_t)t * B + b);
             }
         }
-    };
-    load(T - 1, r, v, dn);
-    for (int t_hi = T - 1; t_hi >= 0; t_hi -= GAE_CHUNK) {
-        load(t_hi - GAE_CHUNK, rn, vn, dnn);   // prefetch the next (earlier) chunk
 #pragma unroll
-        for (int i = 0; i < GAE_CHUNK; ++i) {
+        for (int i = 0; i < CH; ++i) {
             const int t = t_hi - i;
-            if (t >= 0) {
+            if (t >= t0) {
                 const float nt = dn[i] ? 0.0f : 1.0f;
+                const float c = __fmul_rn(gl, nt);
                 const float delta = __fsub_rn(__fadd_rn(r[i], __fmul_rn(__fmul_rn(gamma, next_value), nt)), v[i]);
-                gae = __fadd_rn(delta, __fmul_rn(__fmul_rn(gl, nt), gae));
-                __stcs(adv + (size_t)t * B + b, gae);
-                __stcs(targets + (size_t)t * B + b, __fadd_rn(gae, v[i]));
+                gae = __fadd_rn(delta, __fmul_rn(c, gae));
+                if (WRITE) {
+                    __stcs(adv + (size_t)t * B + b, gae);
+                    __stcs(targets + (size_t)t * B + b, __fadd_rn(gae, v[i]));   // learner:526
+                } else {
+                    aprod = __fmul_rn(aprod, c);
+                }
                 next_value = v[i];
             }
         }
-#pragma unroll
-        for (int i = 0; i < GAE_CHUNK; ++i) { r[i] = rn[i]; v[i] = vn[i]; dn[i] = dnn[i]; }
     }
+}
+
+// One CTA = 32 env columns (lane = column, coalesced) x S time segments (one warp each).  With S > 1
+// every warp first reduces its segment to an affine map (inputs read once from HBM), the maps are
+// composed back to front in shared memory, then each warp replays its segment from its true
+// incoming gae (inputs now L2/L1 hits) and writes advantages and targets.  S = 1 is the plain scan.
+template <int S>
+__global__ void __launch_bounds__(32 * S) gae_kernel(const float* __restrict__ reward, long long rs_t,
+                                                     long long rs_b, const uint8_t* __restrict__ done,
+                                                     const float* __restrict__ value,
+                                                     const float* __restrict__ last_val, float gamma, float gl,
+                                                     float* __restrict__ adv, float* __restrict__ targets, int T,
+                                                     int B, int seg_len) {
+    __shared__ float sA[S][32], sB[S][32];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int b = blockIdx.x * 32 + lane;
+    const bool ok = b < B;
+    const int t0 = min(T, w * seg_len), t1 = min(T, (w + 1) * seg_len);
+    float next_value = 0.0f;
+    if (ok && t0 < t1) next_value = (t1 < T) ? __ldg(value + (size_t)t1 * B + b) : __ldg(last_val + b);
+    float gae_in = 0.0f;
+    if (S > 1) {
+        float bsum = 0.0f, aprod = 1.0f;
+        if (ok && t0 < t1)
+            gae_segment<false, GAE_CHUNK>(reward, rs_t, rs_b, done, value, gamma, gl, adv, targets, B, b, t0, t1, next_value, bsum,
+                               aprod);
+        sA[w][lane] = aprod;
+        sB[w][lane] = bsum;
+        __syncthreads();
+        for (int s2 = S - 1; s2 > w; --s2) gae_in = __fadd_rn(sB[s2][lane], __fmul_rn(sA[s2][lane], gae_in));
+    }
+    float dummy = 1.0f;
+    if (ok && t0 < t1)
+        gae_segment<true, (S == 1 ? GAE_CHUNK_1 : GAE_CHUNK)>(reward, rs_t, rs_b, done, value, gamma, gl, adv, targets, B, b, t0, t1, next_value, gae_in,
+                          dummy);
 }
 
 __global__ void __launch_bounds__(256) adv_stats_kernel(const float* __restrict__ adv, long long count,
@@ -96,7 +129,23 @@ cudaError_t launch_gae(const float* reward, long long rs_t, long long rs_b, cons
                        const float* last_val, float gamma, float gl, float* adv, float* targets, int T, int B,
                        cudaStream_t s) {
     if (T == 0 || B == 0) return cudaSuccess;
-    gae_kernel<<<(B + 63) / 64, 64, 0, s>>>(reward, rs_t, rs_b, done, value, last_val, gamma, gl, adv, targets, T, B);
+    const int grid = (B + 31) / 32;
+    // enough warps to cover HBM latency: >= 8 per SM, segments of at least one load chunk
+    int S = 1;
+    while (S < 32 && grid * S < 148 * 8 && T / (2 * S) >= GAE_CHUNK) S *= 2;
+    const int seg_len = (T + S - 1) / S;
+#define MSAT_GAE_LAUNCH(SS)                                                                                         \
+    gae_kernel<SS><<<grid, 32 * SS, 0, s>>>(reward, rs_t, rs_b, done, value, last_val, gamma, gl, adv, targets, T, B, \
+                                            seg_len)
+    switch (S) {
+        case 1: MSAT_GAE_LAUNCH(1); break;
+        case 2: MSAT_GAE_LAUNCH(2); break;
+        case 4: MSAT_GAE_LAUNCH(4); break;
+        case 8: MSAT_GAE_LAUNCH(8); break;
+        case 16: MSAT_GAE_LAUNCH(16); break;
+        default: MSAT_GAE_LAUNCH(32); break;
+    }
+#undef MSAT_GAE_LAUNCH
     return cudaGetLastError();
 }
 cudaError_t launch_adv_stats(const float* adv, long long count, double* stats, cudaStream_t s) {

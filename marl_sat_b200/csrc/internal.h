@@ -86,5 +86,14 @@ cudaError_t launch_gae(const float* reward, long long rs_t, long long rs_b, cons
                        cudaStream_t s);
 cudaError_t launch_adv_stats(const float* adv, long long count, double* stats, cudaStream_t s);
 cudaError_t launch_adv_normalize(float* adv, long long count, const double* stats, cudaStream_t s);
+cudaError_t launch_gnn_static(const msat_plan* plan, const uint8_t* bank, int P, float* svf, float* a_pos, float* a_neg,
+                              cudaStream_t s);
+cudaError_t launch_gnn_dynamic(const msat_plan* plan, const uint8_t* bank, int P, const uint32_t* state, int B,
+                               int32_t* assign, float* cf, cudaStream_t s);
+cudaError_t launch_rollout_metrics(const float* reward, long long rs_t, long long rs_b, const uint8_t* done,
+                                   const uint8_t* solved, const int32_t* num_unsat, const int32_t* episode_step, int T,
+                                   int B, double* sums, cudaStream_t s);
+cudaError_t launch_eval_track(const msat_plan* plan, const uint32_t* state, const uint8_t* solved, int t, int B,
+                              uint8_t* ever, int32_t* steps, int32_t* solution, cudaStream_t s);
 
 }  // namespace msat

@@ -163,6 +163,23 @@ __device__ __forceinline__ void apply_actions(const Dims& d, const int32_t* __re
     }
 }
 
+// Four observation ints from a 4-bit mask nibble and a 4-bit value nibble: out = mask ? value : -1.
+// The nibbles are spread to one byte per element with a multiply, combined bytewise into
+// {0xFF, 0x00, 0x01} and sign-extended to int32 with one PRMT each.
+__device__ __forceinline__ int4 expand_nibble(uint32_t mn, uint32_t xn) {
+    const uint32_t m4 = (mn * 0x00204081u) & 0x01010101u;          // bit i -> byte i
+    const uint32_t r = 0xFFFFFFFFu - m4 * 0xFFu;                   // byte: mask ? 0x00 : 0xFF
+    const uint32_t c = ((xn * 0x00204081u) & 0x01010101u) | r;     // byte: mask ? value : 0xFF
+    // prmt.b32 selector nibble: bits 2:0 pick the byte, bit 3 replicates its sign instead (the
+    // __byte_perm intrinsic masks bit 3 away, hence inline PTX): byte i sign-extended to 32 bits.
+    int4 v;
+    asm("prmt.b32 %0, %1, %1, 0x8880;" : "=r"(v.x) : "r"(c));
+    asm("prmt.b32 %0, %1, %1, 0x9991;" : "=r"(v.y) : "r"(c));
+    asm("prmt.b32 %0, %1, %1, 0xAAA2;" : "=r"(v.z) : "r"(c));
+    asm("prmt.b32 %0, %1, %1, 0xBBB3;" : "=r"(v.w) : "r"(c));
+    return v;
+}
+
 // Observation writer (env:345-398).  Per env the A*D output ints are one flat range of the
 // [B,A,D] tensor.  out[i] = mask[i] ? value[i] : -1 where mask is the bank's flat bit stream and
 // value is [assign | clause status | assign] repeated per agent.  Both streams are re-based to the
@@ -188,7 +205,9 @@ __device__ __forceinline__ void emit_obs(const Dims& d, int e, const uint32_t* a
         int j = j0 > 0 ? j0 : 0;
         const int jend = (j0 + 32 < d.AD) ? j0 + 32 : d.AD;
         if (j < jend) {
-            int p = j - (j / d.D) * d.D;
+            int arow = (int)__umulhi((uint32_t)j, d.inv_D);     // j / D with a rounded-up reciprocal (+0/+1)
+            if (arow * d.D > j) --arow;
+            int p = j - arow * d.D;
             while (j < jend) {
                 int len = d.D - p;
                 if (len > jend - j) len = jend - j;
@@ -203,27 +222,31 @@ __device__ __forceinline__ void emit_obs(const Dims& d, int e, const uint32_t* a
     }
     group_sync<GS>(gid);
 
+    // ---- streaming stores: chunk q covers ints [4q, 4q+4) of the re-based range ----
     int32_t* out = obs + (g_start - s);
     const int lo_valid = s, hi_valid = s + d.AD;
-    const int nchunks = (hi_valid + 3) >> 2;
-#pragma unroll 4
-    for (int q = gt; q < nchunks; q += GS) {
-        const uint2 mx = smx[q >> 3];
+    const int q_lo = (lo_valid + 3) >> 2;       // first chunk that lies completely inside the env's range
+    const int q_hi = hi_valid >> 2;             // one past the last complete chunk
+    {
+        // GS is a multiple of 8, so a lane keeps the same nibble position in every iteration.
+        int q = q_lo + gt;
         const int sh = (q & 7) * 4;
-        const uint32_t mn = mx.x >> sh, xn = mx.y >> sh;
-        int4 v;
-        v.x = (mn & 1u) ? (int)(xn & 1u) : -1;
-        v.y = (mn & 2u) ? (int)((xn >> 1) & 1u) : -1;
-        v.z = (mn & 4u) ? (int)((xn >> 2) & 1u) : -1;
-        v.w = (mn & 8u) ? (int)((xn >> 3) & 1u) : -1;
-        const int lo = 4 * q;
-        if (lo >= lo_valid && lo + 4 <= hi_valid) {
-            __stcs(reinterpret_cast<int4*>(out + lo), v);
-        } else {
-            if (lo + 0 >= lo_valid && lo + 0 < hi_valid) out[lo + 0] = v.x;
-            if (lo + 1 >= lo_valid && lo + 1 < hi_valid) out[lo + 1] = v.y;
-            if (lo + 2 >= lo_valid && lo + 2 < hi_valid) out[lo + 2] = v.z;
-            if (lo + 3 >= lo_valid && lo + 3 < hi_valid) out[lo + 3] = v.w;
+        const uint2* sp = smx + (q >> 3);
+        int4* op = reinterpret_cast<int4*>(out) + q;
+#pragma unroll 4
+        for (; q < q_hi; q += GS, sp += GS / 8, op += GS) {
+            const uint2 mx = *sp;
+            __stcs(op, expand_nibble((mx.x >> sh) & 0xFu, (mx.y >> sh) & 0xFu));
+        }
+    }
+    // at most one partial chunk at each end (the env's range is only 4-byte aligned): scalar stores
+    if (gt < 8) {
+        const int q = (gt < 4) ? q_lo - 1 : q_hi;
+        const int i = 4 * q + (gt & 3);
+        const bool partial = (gt < 4) ? (4 * q_lo != lo_valid) : (4 * q_hi != hi_valid);
+        if (partial && q >= 0 && i >= lo_valid && i < hi_valid) {
+            const uint2 mx = smx[i >> 5];
+            out[i] = ((mx.x >> (i & 31)) & 1u) ? (int)((mx.y >> (i & 31)) & 1u) : -1;
         }
     }
 }
