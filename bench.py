@@ -213,7 +213,6 @@ def main_ours(args):
     import torch.distributed as dist
 
     import marl_sat_b200 as M
-    from oracle import threefry as otf   # PRNGKey(seed) constructor only ([0, seed]); no compute
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -240,7 +239,7 @@ def main_ours(args):
     problems = torch.from_numpy(make_formulas(w, P, 20261018 + 2))
     bank = env.make_bank(problems)
     del problems
-    vec = M.VecSATEnv(env, bank, Bg, otf.prng_key(SEED), world_size=shard_world, rank=shard_rank)
+    vec = M.VecSATEnv(env, bank, Bg, M.prng_key(SEED), world_size=shard_world, rank=shard_rank)
     B = vec.num_envs
     A, V = env.num_agents, env.max_vars_per_agent
     gen = torch.Generator(device=dev).manual_seed(1234 + shard_rank)
@@ -265,13 +264,34 @@ def main_ours(args):
     for i in range(W):
         vec.step(actions[i % ACTION_CYCLE])
     torch.cuda.synchronize()
+    graph = None
+    if args.graph > 0:
+        # launch-bound regime (small per-GPU batches): capture a block of G rollout steps (G even, so the
+        # ping-pong rng buffers end where they started) and replay it; the remainder is launched directly
+        G = max(2, args.graph - args.graph % 2)
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            for i in range(G):
+                vec.step(actions[i % ACTION_CYCLE])
+        torch.cuda.synchronize()
+
+    def run_steps(count, first):
+        if graph is None:
+            for i in range(count):
+                vec.step(actions[(first + i) % ACTION_CYCLE])
+            return
+        reps, rem = divmod(count, G)
+        for _ in range(reps):
+            graph.replay()
+        for i in range(rem):
+            vec.step(actions[i % ACTION_CYCLE])
+
     barrier()
     torch.cuda.synchronize()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t_wall0 = time.perf_counter()
     ev0.record()
-    for i in range(K):
-        vec.step(actions[(W + i) % ACTION_CYCLE])
+    run_steps(K, W)
     ev1.record()
     torch.cuda.synchronize()
     t_wall1 = time.perf_counter()
@@ -397,6 +417,7 @@ def main_ours(args):
                                    f"{P} distinct formulas, max_steps {MAX_STEPS}, auto-reset on, action_mode 0",
                        "envs_global": Bg, "envs_per_gpu": B, "problems": P,
                        "group_threads": bank.plan.dims.group_threads,
+                       "launch": f"CUDA graph of {G} steps" if graph is not None else "one kernel launch per step",
                        "l2": f"no flush: each step writes {B * A * env.obs_dim * 4 / 1e6:.0f} MB of observations per GPU "
                              f"(> 126 MB L2) and cycles {ACTION_CYCLE} action batches"},
             "clocks": sampler.summary(t_wall0, t_wall1),
@@ -443,6 +464,8 @@ def parse_args(argv=None):
     ap.add_argument("--cpu-envs-per-core", type=int, default=128)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-gae", action="store_true")
+    ap.add_argument("--graph", type=int, default=0, metavar="G",
+                    help="replay the rollout steps as CUDA graphs of G steps each (0 = plain launches)")
     ap.add_argument("--gae-steps", type=int, default=512, help="T of the GAE leg (configs/MAPPO_CONFIG.yaml NUM_STEPS)")
     ap.add_argument("--emulate-shard", type=int, nargs=2, metavar=("WORLD", "RANK"), default=None,
                     help="debug: single process, but own the env shard of RANK out of WORLD")

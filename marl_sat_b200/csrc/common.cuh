@@ -23,6 +23,10 @@ enum { ST_STEP = 0, ST_PIDX = 1, ST_NUNSAT = 2, ST_FLAGS = 3 };
 
 constexpr uint16_t LIT_PAD = 0xFFFFu;   // literal code of a 0-padding literal (never true)
 
+// Literal codes are stored literal-major ([k][m]) inside a bank record: consecutive lanes = consecutive
+// clauses read consecutive u16 (conflict-free shared-memory loads).
+__host__ __device__ __forceinline__ int lit_index(int m, int c, int j) { return j * m + c; }
+
 // ---- agent grouping (env:294-338; contiguous balanced split) --------------
 __host__ __device__ __forceinline__ int group_size(const Dims& d, int a) { return d.base + (a < d.rem ? 1 : 0); }
 __host__ __device__ __forceinline__ int group_start(const Dims& d, int a) { return a * d.base + (a < d.rem ? a : d.rem); }
@@ -130,7 +134,8 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)_
 
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    // make the initialised barrier visible to the async (TMA) proxy; CTA scope is enough without clusters
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 }
 __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");

@@ -23,7 +23,7 @@ __global__ void __launch_bounds__(256) gnn_static_kernel(const Dims d, const uin
     __syncthreads();
     for (int c = tid; c < d.m; c += nt) {            // one thread owns column c of A_pos / A_neg
         for (int j = 0; j < d.k; ++j) {
-            const uint32_t code = lits[c * d.k + j];
+            const uint32_t code = lits[lit_index(d.m, c, j)];
             if (code == LIT_PAD) continue;
             const int v = (int)(code >> 1), neg = (int)(code & 1u);
             atomicAdd(&deg[neg * d.n + v], 1);
@@ -58,7 +58,7 @@ __global__ void __launch_bounds__(128) gnn_dynamic_kernel(const Dims d, const ui
         for (int c = tid; c < d.m; c += nt) {
             int ntrue = 0;
             for (int j = 0; j < d.k; ++j) {
-                const uint32_t code = lits[c * d.k + j];
+                const uint32_t code = lits[lit_index(d.m, c, j)];
                 if (code != LIT_PAD) {
                     const uint32_t v = code >> 1;
                     ntrue += (int)(((st[v >> 5] >> (v & 31)) ^ code) & 1u);

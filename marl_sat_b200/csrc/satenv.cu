@@ -9,7 +9,7 @@ namespace msat {
 // K_compile: one CTA per formula.  Evaluates the agent<->clause and agent<->neighbour
 // relations of _compute_observation_maps (env:99-128) once per formula and stores them as a
 // flat A*D-bit mask stream in observation order [own(n) | clauses(m) | neighbours(n)] per agent,
-// next to the literals packed as u16 codes ((var << 1) | negated, 0xFFFF for a 0 padding literal).
+// next to the literals packed literal-major as u16 codes ((var << 1) | negated, 0xFFFF for a 0 padding literal).
 // =====================================================================================
 __global__ void __launch_bounds__(256) compile_bank_kernel(Dims d, const int32_t* __restrict__ clauses,
                                                            uint8_t* __restrict__ bank) {
@@ -46,14 +46,14 @@ __global__ void __launch_bounds__(256) compile_bank_kernel(Dims d, const int32_t
                 const int a = var_to_agent(d, v);
                 ca[a >> 5] |= 1u << (a & 31);
             }
-            lits[c * d.k + j] = code;
+            lits[lit_index(d.m, c, j)] = code;
         }
     }
     __syncthreads();
     // env:116-121: every real variable of a related clause is a candidate neighbour.
     for (int c = tid; c < d.m; c += nt) {
         for (int j = 0; j < d.k; ++j) {
-            const uint16_t code = lits[c * d.k + j];
+            const uint16_t code = lits[lit_index(d.m, c, j)];
             if (code == LIT_PAD) continue;
             const int v = code >> 1;
             for (int w = 0; w < d.agw; ++w) {
@@ -89,6 +89,22 @@ __global__ void __launch_bounds__(256) compile_bank_kernel(Dims d, const int32_t
 // =====================================================================================
 
 // Clause truth via warp ballots (env:130-156): lane = clause, ballot word = 32 clause-status bits.
+// One literal: true <=> assignment bit != negation flag; a 0 padding literal is never true (env:141-144).
+__device__ __forceinline__ bool literal_true(uint32_t code, const uint32_t* assign) {
+    const uint32_t v = code >> 1;
+    return code != LIT_PAD && (((assign[v >> 5] >> (v & 31)) ^ code) & 1u) != 0u;
+}
+template <int K>
+__device__ __forceinline__ bool clause_true_fixed(const uint16_t* lits, int m, int c, const uint32_t* assign) {
+    uint32_t code[K];
+#pragma unroll
+    for (int j = 0; j < K; ++j) code[j] = lits[lit_index(m, c, j)];     // independent loads first
+    bool sat = false;
+#pragma unroll
+    for (int j = 0; j < K; ++j) sat |= literal_true(code[j], assign);
+    return sat;
+}
+
 template <int GS>
 __device__ __forceinline__ void eval_clauses(const Dims& d, const uint16_t* lits, const uint32_t* assign,
                                              uint32_t* satw, int* nunsat, int gt) {
@@ -99,13 +115,11 @@ __device__ __forceinline__ void eval_clauses(const Dims& d, const uint16_t* lits
         const bool valid = c < d.m;
         bool sat = false;
         if (valid) {
-            const uint16_t* L = lits + c * d.k;
-            for (int j = 0; j < d.k; ++j) {
-                const uint32_t code = L[j];
-                if (code != LIT_PAD) {
-                    const uint32_t v = code >> 1;
-                    sat |= (((assign[v >> 5] >> (v & 31)) ^ code) & 1u) != 0u;   // true <=> assignment bit != negation flag
-                }
+            if (d.k == 3) {
+                sat = clause_true_fixed<3>(lits, d.m, c, assign);
+            } else {
+#pragma unroll 4
+                for (int j = 0; j < d.k; ++j) sat |= literal_true(lits[lit_index(d.m, c, j)], assign);
             }
         }
         const uint32_t word = __ballot_sync(0xffffffffu, valid && sat);
@@ -454,7 +468,7 @@ __global__ void __launch_bounds__(128) export_kernel(const Dims d, const ExportA
         for (int c = tid; c < d.m; c += nt) {
             bool sat = false;
             for (int j = 0; j < d.k; ++j) {
-                const uint32_t code = lits[c * d.k + j];
+                const uint32_t code = lits[lit_index(d.m, c, j)];
                 if (code != LIT_PAD) {
                     const uint32_t v = code >> 1;
                     sat |= (((st[v >> 5] >> (v & 31)) ^ code) & 1u) != 0u;
@@ -471,7 +485,7 @@ __global__ void __launch_bounds__(128) export_kernel(const Dims d, const ExportA
         for (int i = tid; i < d.A; i += nt) a.done[(size_t)e * d.A + i] = (uint8_t)(tail[ST_FLAGS] & 1u);
     if (a.clauses || a.l2a)
         for (int i = tid; i < d.m * d.k; i += nt) {
-            const uint32_t code = lits[i];
+            const uint32_t code = lits[lit_index(d.m, i / d.k, i % d.k)];
             const int v = (code == LIT_PAD) ? -1 : (int)(code >> 1);
             if (a.clauses) a.clauses[(size_t)e * d.m * d.k + i] = v < 0 ? 0 : ((code & 1u) ? -(v + 1) : (v + 1));
             // env:160: index -1 wraps to the last variable

@@ -28,6 +28,12 @@ from . import _lib
 from .env import FormulaBank, SATEnv, SATState, _ptr, _stream_ptr, as_u32_tensor
 
 
+def prng_key(seed: int):
+    """``jax.random.PRNGKey(seed)`` as a legacy uint32[2] key: ``[seed >> 32, seed & 0xFFFFFFFF]``."""
+    import numpy as np
+    return np.array([(seed >> 32) & 0xFFFFFFFF, seed & 0xFFFFFFFF], dtype=np.uint32)
+
+
 def shard_range(num_envs_global: int, world_size: int, rank: int):
     """Contiguous block ``[offset, offset + count)`` of the global env batch owned by ``rank``."""
     base, rem = divmod(num_envs_global, world_size)

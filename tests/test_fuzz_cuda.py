@@ -1,0 +1,99 @@
+"""Seeded differential fuzzing of the CUDA path against the oracle over random shapes: odd sizes that
+are not multiples of 32, observation rows shorter than one mask word, more than 32 agents (multi-word
+agent sets), clauses with repeated variables and all-padding clauses, single-literal clauses, tiny and
+empty batches, max_steps = 1, both action modes, every thread-group size."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import rollout as orollout
+from oracle import threefry as otf
+from oracle.sat_env import SATEnvOracle
+from tests.util import assert_obs_equal, assert_state_equal, to_np
+
+pytestmark = pytest.mark.gpu
+
+
+def _random_formulas(rng, B, n, m, k):
+    """Unstructured literals in [-n, n]: repeated variables, x and -x together, zeros anywhere."""
+    cl = rng.integers(-n, n + 1, size=(B, m, k)).astype(np.int32)
+    cl[rng.random((B, m)) < 0.05] = 0                      # some all-padding clauses
+    return cl
+
+
+@pytest.mark.parametrize("seed", range(24))
+def test_random_shapes(seed):
+    import marl_sat_b200 as M
+    rng = np.random.default_rng(1000 + seed)
+    n = int(rng.integers(1, 90))
+    m = int(rng.integers(1, 200))
+    k = int(rng.integers(1, 6))
+    vpa = [None, 1, 2, 3, 5, 7][int(rng.integers(0, 6))]
+    if vpa is not None and vpa > n:
+        vpa = n
+    mode = int(rng.integers(0, 2))
+    B = int(rng.integers(1, 40))
+    gs = [0, 32, 64, 128, 256][seed % 5]
+    max_steps = int(rng.integers(1, 4))
+    cl = _random_formulas(rng, B, n, m, k)
+    keys = rng.integers(0, 2 ** 32, size=(B, 2), dtype=np.uint64).astype(np.uint32)
+    ref = SATEnvOracle(n, m, max_steps, vars_per_agent=vpa, action_mode=mode)
+    env = M.SATEnv(n, m, max_steps, vars_per_agent=vpa, action_mode=mode, verbose=False, group_threads=gs)
+    obs_r, st_r = ref.reset(cl, keys)
+    obs_c, st_c = env.reset(cl, keys)
+    what = f"[n={n} m={m} k={k} vpa={vpa} mode={mode} B={B} gs={gs}] "
+    assert_obs_equal(obs_c, obs_r, env.agents, what + "reset ")
+    assert_state_equal(st_c, st_r, what + "reset ")
+    A, V = ref.num_agents, ref.max_vars_per_agent
+    for t in range(3):
+        acts = (rng.integers(-1, V + 2, size=(B, A)) if mode == 0 else rng.integers(0, 2, size=(B, A, V))).astype(np.int32)
+        obs_r, st_r, rew_r, done_r, info_r = ref.step_env(None, st_r, acts)
+        obs_c, st_c, rew_c, done_c, info_c = env.step_env(None, st_c, acts)
+        assert_obs_equal(obs_c, obs_r, env.agents, what + f"step {t} ")
+        assert_state_equal(st_c, st_r, what + f"step {t} ")
+        assert np.array_equal(to_np(rew_c[env.agents[-1]]), rew_r[ref.agents[-1]])
+        assert np.array_equal(to_np(done_c["__all__"]), done_r["__all__"])
+        assert np.array_equal(to_np(info_c["num_unsatisfied"]), info_r["num_unsatisfied"])
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_random_rollouts_with_autoreset(seed):
+    import marl_sat_b200 as M
+    rng = np.random.default_rng(77 + seed)
+    n, m = int(rng.integers(4, 60)), int(rng.integers(5, 120))
+    B, P = int(rng.integers(1, 50)), int(rng.integers(1, 9))
+    vpa = [None, 3, 6][seed % 3]
+    max_steps = int(rng.integers(1, 4))
+    problems = _random_formulas(rng, P, n, m, 3)
+    ref = SATEnvOracle(n, m, max_steps, vars_per_agent=vpa)
+    env = M.SATEnv(n, m, max_steps, vars_per_agent=vpa, verbose=False)
+    key0 = otf.prng_key(seed)
+    vec = M.VecSATEnv(env, problems, B, key0)
+    obs_c = vec.reset()
+    key, idx0, rk0 = orollout.initial_reset_inputs(key0, B, P)
+    obs_r, st_r = ref.reset(problems[idx0], rk0)
+    assert np.array_equal(to_np(obs_c), np.stack([obs_r[a] for a in ref.agents], 1))
+    for t in range(6):
+        acts = rng.integers(0, ref.max_vars_per_agent + 1, size=(B, ref.num_agents)).astype(np.int32)
+        ks = orollout.rollout_keys(key, B, P)
+        key = ks["rng"]
+        fo, st_r, rew_r, done_r, info_r = orollout.env_step_with_autoreset(
+            ref, st_r, acts, problems, ks["new_problem_indices"], ks["reset_keys"])
+        out = vec.step(torch.from_numpy(acts).cuda())
+        assert np.array_equal(to_np(out["obs"]), fo), f"step {t}"
+        assert np.array_equal(to_np(out["done"][:, -1]).astype(bool), done_r)
+        assert_state_equal(vec.sat_state(), st_r, f"step {t} ")
+
+
+def test_empty_batch_is_a_no_op():
+    import marl_sat_b200 as M
+    env = M.SATEnv(20, 91, 5, verbose=False)
+    from marl_sat_b200.synth import uniform_ksat
+    bank = env.make_bank(uniform_ksat(3, 20, 91, 3, 0))
+    idx = torch.empty((0,), dtype=torch.int32, device="cuda")
+    keys = torch.empty((0, 2), dtype=torch.int32, device="cuda")
+    obs, st = env.reset_from_bank(bank, idx, keys)
+    assert obs.shape == (0, 5, 131) and st.num_envs == 0
+    adv, tgt = M.calculate_gae(torch.empty((0, 4), device="cuda"), torch.empty((0, 4), dtype=torch.uint8, device="cuda"),
+                               torch.empty((0, 4), device="cuda"), torch.zeros(4, device="cuda"), 0.9, 0.9)
+    assert adv.shape == (0, 4)
