@@ -60,7 +60,9 @@ int msat_plan_create(msat_plan** out, int32_t n, int32_t m, int32_t k, int32_t A
 
     const int chunks = (d.AD + 3) / 4;
     int gs = group_threads;
-    if (gs == 0) gs = chunks <= 256 ? 32 : (chunks <= 1024 ? 64 : (chunks <= 2560 ? 128 : 256));
+    // measured on B200 (profiles/r1_group_size_sweep.md): about 16-24 store iterations per thread is the sweet
+    // spot -- larger groups idle most lanes in the short per-env phases, smaller ones serialise the stores
+    if (gs == 0) gs = chunks <= 768 ? 32 : (chunks <= 1536 ? 64 : (chunks <= 3072 ? 128 : 256));
     if (gs != 32 && gs != 64 && gs != 128 && gs != 256) { delete p; return MSAT_EINVAL; }
     const GroupLayout L = group_layout(d);
     // grow the group until one CTA's groups fit in shared memory

@@ -163,13 +163,25 @@ __device__ __forceinline__ void tma_load_1d(void* smem_dst, const void* gmem_src
 }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
-// Barrier over the GS threads that cooperate on one env.
+// Barrier over the GS threads that cooperate on one env.  The named-barrier index must be an
+// immediate: with a register index ptxas reserves all 16 hardware barriers for the CTA, which caps
+// the number of resident CTAs per SM.
 template <int GS>
 __device__ __forceinline__ void group_sync(int gid) {
     if constexpr (GS == 32) {
         __syncwarp();
+    } else if constexpr (GS == 256) {
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+    } else if constexpr (GS == 128) {
+        if (gid == 0) asm volatile("bar.sync 1, 128;" ::: "memory");
+        else asm volatile("bar.sync 2, 128;" ::: "memory");
     } else {
-        asm volatile("bar.sync %0, %1;" ::"r"(gid + 1), "n"(GS) : "memory");
+        switch (gid) {
+            case 0: asm volatile("bar.sync 1, 64;" ::: "memory"); break;
+            case 1: asm volatile("bar.sync 2, 64;" ::: "memory"); break;
+            case 2: asm volatile("bar.sync 3, 64;" ::: "memory"); break;
+            default: asm volatile("bar.sync 4, 64;" ::: "memory"); break;
+        }
     }
 }
 
