@@ -252,8 +252,14 @@ def main_ours(args):
             dist.barrier()
 
     K, W = args.steps, args.warmup
-    # pinned host buffers of the e2e leg are allocated up front (no allocation between timed regions)
-    host = vec.alloc_host_io()
+    # e2e leg: same envs API with compact outputs (one reward / done value per env: every agent's is the same
+    # scalar, env:196,260, and the host side re-expands them as views); it shares the observation buffer.
+    # Pinned host buffers are allocated up front (no allocation between timed regions).
+    vec_h = M.VecSATEnv(env, bank, Bg, M.prng_key(SEED + 1), world_size=shard_world, rank=shard_rank, emit_obs=False,
+                        compact_outputs=True)
+    vec_h.out["obs"] = vec.out["obs"]
+    vec_h.reset()
+    host = vec_h.alloc_host_io()
     host_actions = [actions[i].cpu().pin_memory() for i in range(4)]
     torch.cuda.synchronize()
     sampler = ClockSampler(local_rank) if rank == 0 else None
@@ -319,34 +325,35 @@ def main_ours(args):
     Ke = max(1, min(K, args.e2e_steps))
     for i in range(2):
         host["actions"].copy_(host_actions[i % 4])
-        vec.step_host(host)
+        vec_h.step_host(host)
     torch.cuda.synchronize()
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for i in range(Ke):
         host["actions"] = host_actions[i % 4]
-        vec.step_host(host)
-        _ = int(host["solved"][0])          # the host reads the step's result
+        vec_h.step_host(host)
+        rewards, dones, infos = vec_h.host_views(host)      # reference-shaped dicts (views)
+        _ = int(infos["solved"][0]) + int(dones["__all__"][0])   # the host reads the step's result
     e1.record()
     torch.cuda.synchronize()
     barrier()
     e2e_ms = e0.elapsed_time(e1)
     h2d = B * A * 4
-    d2h = B * (4 * A + (A + 1) + 1 + 4 + 4)
+    d2h = B * (4 + 1 + 1 + 4 + 4)           # team reward, done, solved, num_unsatisfied, episode_step
 
     # optional: also bring the observations to the host (PCIe-bound; reported separately)
     e2e_obs = None
     if args.e2e_obs_steps > 0 and world == 1:
         obs_host = torch.empty(vec.out["obs"].shape, dtype=torch.int32, pin_memory=True)
         o0, o1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        vec.step_host(host)
+        vec_h.step_host(host)
         obs_host.copy_(vec.out["obs"], non_blocking=True)
         torch.cuda.synchronize()
         barrier()
         o0.record()
         for i in range(args.e2e_obs_steps):
-            vec.step_host(host)
+            vec_h.step_host(host)
             obs_host.copy_(vec.out["obs"], non_blocking=True)
             torch.cuda.synchronize()
         o1.record()
@@ -423,9 +430,10 @@ def main_ours(args):
             "clocks": sampler.summary(t_wall0, t_wall1),
             "e2e": {"value": Bg * Ke / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d * world,
                     "d2h_bytes_per_step": d2h * world, "steps": Ke,
-                    "what": "VecSATEnv.step_host -> msat_step_host: pinned host actions in; reward, done, solved, "
-                            "num_unsatisfied, episode_step out to pinned host memory and read by the host every step; "
-                            "observations stay in HBM for the policy"},
+                    "what": "VecSATEnv.step_host -> msat_rollout_step_host: pinned host actions in; team reward, done, "
+                            "solved, num_unsatisfied, episode_step out to pinned host memory, expanded to the "
+                            "reference's per-agent dicts as views and read by the host every step; observations "
+                            "stay in HBM for the policy"},
             "gpu_launches": launches,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "peak_source": peak_src, "kernel": "msat::env_kernel<GS, MODE_STEP>",

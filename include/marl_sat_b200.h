@@ -105,7 +105,9 @@ int msat_reset(const msat_plan* plan, const void* bank, int32_t num_problems,
  *                  finish this step and only when auto_reset != 0 (else may be NULL)
  *   obs            int32 [B, A, D] of the state the caller continues from (the
  *                  post-reset state for finished envs when auto_reset != 0); NULL = skip
- *   reward         float [B, A]    (env:183-198: 1.0 when solved else 0.0, all agents)
+ *   reward         float [B, reward_cols]: 1.0 when solved else 0.0 (env:183-198), the same scalar
+ *                  repeated reward_cols times per env (A = one per agent, env:196; 1 = the shared
+ *                  team reward only, which is all the GAE reads, learner:514)
  *   done           uint8 [B, done_cols]: the episode-end flag repeated done_cols times per env
  *                  (A+1 = one per agent plus "__all__", env:260-261; 1 = Transition.global_done
  *                  only, learner:468); pre-reset values
@@ -114,8 +116,8 @@ int msat_reset(const msat_plan* plan, const void* bank, int32_t num_problems,
 int msat_step(const msat_plan* plan, const void* bank, int32_t num_problems,
               const uint32_t* state_in, uint32_t* state_out, const int32_t* actions,
               int32_t auto_reset, const int32_t* new_problem_idx, const uint32_t* reset_keys,
-              int32_t* obs, float* reward, uint8_t* done, int32_t done_cols, uint8_t* solved,
-              int32_t* num_unsatisfied, int32_t* episode_step,
+              int32_t* obs, float* reward, int32_t reward_cols, uint8_t* done, int32_t done_cols,
+              uint8_t* solved, int32_t* num_unsatisfied, int32_t* episode_step,
               int32_t num_envs, void* stream);
 
 /* One whole rollout step of the learner's `_env_step` env half (learner:397-464) in ONE launch:
@@ -129,8 +131,8 @@ int msat_rollout_step(const msat_plan* plan, const void* bank, int32_t num_probl
                       const uint32_t* state_in, uint32_t* state_out, const int32_t* actions,
                       const uint32_t* rng_in, uint32_t* chain_out,
                       int32_t num_envs_global, int32_t env_offset,
-                      int32_t* obs, float* reward, uint8_t* done, int32_t done_cols, uint8_t* solved,
-                      int32_t* num_unsatisfied, int32_t* episode_step,
+                      int32_t* obs, float* reward, int32_t reward_cols, uint8_t* done, int32_t done_cols,
+                      uint8_t* solved, int32_t* num_unsatisfied, int32_t* episode_step,
                       int32_t num_envs, void* stream);
 
 /* Replaces `SATEnv.get_obs(state)` (env:345-398): obs int32[B,A,D] from a state. */
@@ -150,19 +152,21 @@ int msat_export_state(const msat_plan* plan, const void* bank, int32_t num_probl
                       int32_t* agent_clause_masks, int32_t* agent_neighbor_masks,
                       int32_t* literal_to_agent_idx, int32_t* problem_idx, void* stream);
 
-/* Host-buffer convenience wrapper around msat_step for callers that keep actions
- * and results in (pinned) host memory: copies `actions_host` to `actions_dev`,
- * steps, copies reward/done/solved/num_unsatisfied/episode_step back into the
- * `*_host` buffers (each may be NULL) and synchronises the stream.  All device
- * workspaces are caller-owned.  obs stays on the device (obs_dev). */
-int msat_step_host(const msat_plan* plan, const void* bank, int32_t num_problems,
-                   uint32_t* state, const int32_t* actions_host, int32_t* actions_dev,
-                   int32_t auto_reset, const int32_t* new_problem_idx, const uint32_t* reset_keys,
-                   int32_t* obs_dev, float* reward_dev, uint8_t* done_dev, int32_t done_cols, uint8_t* solved_dev,
-                   int32_t* num_unsatisfied_dev, int32_t* episode_step_dev,
-                   float* reward_host, uint8_t* done_host, uint8_t* solved_host,
-                   int32_t* num_unsatisfied_host, int32_t* episode_step_host,
-                   int32_t num_envs, void* stream);
+/* Host-buffer entry point of one rollout step (msat_rollout_step) for callers that keep actions and
+ * results in (pinned) host memory: copies `actions_host` to `actions_dev`, runs the fused step
+ * (rng chain + key derivation + step + auto-reset), copies reward / done / solved / num_unsatisfied /
+ * episode_step back into the `*_host` buffers (each may be NULL) and synchronises the stream.  All
+ * device workspaces are caller-owned; observations stay on the device (obs_dev). */
+int msat_rollout_step_host(const msat_plan* plan, const void* bank, int32_t num_problems,
+                           uint32_t* state, const int32_t* actions_host, int32_t* actions_dev,
+                           const uint32_t* rng_in, uint32_t* chain_out,
+                           int32_t num_envs_global, int32_t env_offset,
+                           int32_t* obs_dev, float* reward_dev, int32_t reward_cols,
+                           uint8_t* done_dev, int32_t done_cols, uint8_t* solved_dev,
+                           int32_t* num_unsatisfied_dev, int32_t* episode_step_dev,
+                           float* reward_host, uint8_t* done_host, uint8_t* solved_host,
+                           int32_t* num_unsatisfied_host, int32_t* episode_step_host,
+                           int32_t num_envs, void* stream);
 
 /* --- rollout RNG chain (JAX 0.4.29 Threefry-2x32, non-partitionable) --------- */
 

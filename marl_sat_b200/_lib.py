@@ -41,11 +41,11 @@ SIGNATURES = {
     "msat_plan_dims": (C.c_int, [_p, C.POINTER(Dims)]),
     "msat_compile_bank": (C.c_int, [_p, _p, _i32, _p, _p]),
     "msat_reset": (C.c_int, [_p, _p, _i32, _p, _p, _p, _p, _i32, _p]),
-    "msat_step": (C.c_int, [_p, _p, _i32, _p, _p, _p, _i32, _p, _p, _p, _p, _p, _i32, _p, _p, _p, _i32, _p]),
-    "msat_rollout_step": (C.c_int, [_p, _p, _i32, _p, _p, _p, _p, _p, _i32, _i32, _p, _p, _p, _i32, _p, _p, _p, _i32, _p]),
+    "msat_step": (C.c_int, [_p, _p, _i32, _p, _p, _p, _i32, _p, _p, _p, _p, _i32, _p, _i32, _p, _p, _p, _i32, _p]),
+    "msat_rollout_step": (C.c_int, [_p, _p, _i32, _p, _p, _p, _p, _p, _i32, _i32, _p, _p, _i32, _p, _i32, _p, _p, _p, _i32, _p]),
     "msat_get_obs": (C.c_int, [_p, _p, _i32, _p, _p, _i32, _p]),
     "msat_export_state": (C.c_int, [_p, _p, _i32, _p, _i32] + [_p] * 10 + [_p]),
-    "msat_step_host": (C.c_int, [_p, _p, _i32, _p, _p, _p, _i32, _p, _p, _p, _p, _p, _i32, _p, _p, _p] + [_p] * 5 + [_i32, _p]),
+    "msat_rollout_step_host": (C.c_int, [_p, _p, _i32, _p, _p, _p, _p, _p, _i32, _i32, _p, _p, _i32, _p, _i32, _p, _p, _p] + [_p] * 5 + [_i32, _p]),
     "msat_rng_chain": (C.c_int, [_p, _p, _p]),
     "msat_rng_split2": (C.c_int, [_p, _p, _p]),
     "msat_env_keys": (C.c_int, [_p, _p, _i32, _i32, _i32, _i32, _p, _p, _p]),

@@ -108,9 +108,9 @@ int msat_reset(const msat_plan* plan, const void* bank, int32_t P, const int32_t
 
 int msat_step(const msat_plan* plan, const void* bank, int32_t P, const uint32_t* state_in, uint32_t* state_out,
               const int32_t* actions, int32_t auto_reset, const int32_t* new_problem_idx, const uint32_t* reset_keys,
-              int32_t* obs, float* reward, uint8_t* done, int32_t done_cols, uint8_t* solved,
+              int32_t* obs, float* reward, int32_t reward_cols, uint8_t* done, int32_t done_cols, uint8_t* solved,
               int32_t* num_unsatisfied, int32_t* episode_step, int32_t B, void* stream) {
-    if (!plan || B < 0 || P <= 0 || (done && done_cols <= 0)) return MSAT_EINVAL;
+    if (!plan || B < 0 || P <= 0 || (done && done_cols <= 0) || (reward && reward_cols <= 0)) return MSAT_EINVAL;
     if (B > 0 && (!bank || !state_in || !state_out || !actions)) return MSAT_EINVAL;
     if (auto_reset && B > 0 && (!new_problem_idx || !reset_keys)) return MSAT_EINVAL;
     if (!aligned(bank, 128) || !aligned(state_in, 16) || !aligned(state_out, 16) || !aligned(obs, 16))
@@ -119,16 +119,18 @@ int msat_step(const msat_plan* plan, const void* bank, int32_t P, const uint32_t
     a.bank = static_cast<const uint8_t*>(bank); a.P = P;
     a.state_in = state_in; a.state_out = state_out; a.actions = actions;
     a.auto_reset = auto_reset ? 1 : 0; a.prob_idx = new_problem_idx; a.keys = reset_keys;
-    a.obs = obs; a.reward = reward; a.done = done; a.done_cols = done_cols; a.solved = solved;
+    a.obs = obs; a.reward = reward; a.reward_cols = reward_cols; a.done = done; a.done_cols = done_cols;
+    a.solved = solved;
     a.num_unsat = num_unsatisfied; a.episode_step = episode_step; a.B = B;
     return cuda_rc(launch_env(plan, MODE_STEP, a, (cudaStream_t)stream));
 }
 
 int msat_rollout_step(const msat_plan* plan, const void* bank, int32_t P, const uint32_t* state_in,
                       uint32_t* state_out, const int32_t* actions, const uint32_t* rng_in, uint32_t* chain_out,
-                      int32_t Bg, int32_t env_offset, int32_t* obs, float* reward, uint8_t* done, int32_t done_cols,
-                      uint8_t* solved, int32_t* num_unsatisfied, int32_t* episode_step, int32_t B, void* stream) {
-    if (!plan || B < 0 || P <= 0 || (done && done_cols <= 0)) return MSAT_EINVAL;
+                      int32_t Bg, int32_t env_offset, int32_t* obs, float* reward, int32_t reward_cols, uint8_t* done,
+                      int32_t done_cols, uint8_t* solved, int32_t* num_unsatisfied, int32_t* episode_step, int32_t B,
+                      void* stream) {
+    if (!plan || B < 0 || P <= 0 || (done && done_cols <= 0) || (reward && reward_cols <= 0)) return MSAT_EINVAL;
     if (!rng_in || !chain_out || Bg <= 0 || env_offset < 0 || (long long)env_offset + B > Bg) return MSAT_EINVAL;
     if (Bg > (1 << 30)) return MSAT_EUNSUPPORTED;
     {   // the advanced chain is written while other CTAs still read rng_in: the buffers must not overlap
@@ -142,7 +144,8 @@ int msat_rollout_step(const msat_plan* plan, const void* bank, int32_t P, const 
     a.bank = static_cast<const uint8_t*>(bank); a.P = P;
     a.state_in = state_in; a.state_out = state_out; a.actions = actions;
     a.auto_reset = 1; a.rng_in = rng_in; a.chain_out = chain_out; a.Bg = (uint32_t)Bg; a.env_off = (uint32_t)env_offset;
-    a.obs = obs; a.reward = reward; a.done = done; a.done_cols = done_cols; a.solved = solved;
+    a.obs = obs; a.reward = reward; a.reward_cols = reward_cols; a.done = done; a.done_cols = done_cols;
+    a.solved = solved;
     a.num_unsat = num_unsatisfied; a.episode_step = episode_step; a.B = B;
     if (B == 0) return cuda_rc(launch_rng_chain(rng_in, chain_out, (cudaStream_t)stream));
     return cuda_rc(launch_env(plan, MODE_STEP, a, (cudaStream_t)stream));
@@ -174,32 +177,38 @@ int msat_export_state(const msat_plan* plan, const void* bank, int32_t P, const 
     return cuda_rc(launch_export(plan, a, (cudaStream_t)stream));
 }
 
-int msat_step_host(const msat_plan* plan, const void* bank, int32_t P, uint32_t* state, const int32_t* actions_host,
-                   int32_t* actions_dev, int32_t auto_reset, const int32_t* new_problem_idx,
-                   const uint32_t* reset_keys, int32_t* obs_dev, float* reward_dev, uint8_t* done_dev,
-                   int32_t done_cols, uint8_t* solved_dev, int32_t* num_unsatisfied_dev, int32_t* episode_step_dev, float* reward_host,
-                   uint8_t* done_host, uint8_t* solved_host, int32_t* num_unsatisfied_host,
-                   int32_t* episode_step_host, int32_t B, void* stream) {
-    if (!plan || !actions_host || !actions_dev) return MSAT_EINVAL;
+int msat_rollout_step_host(const msat_plan* plan, const void* bank, int32_t P, uint32_t* state,
+                           const int32_t* actions_host, int32_t* actions_dev, const uint32_t* rng_in,
+                           uint32_t* chain_out, int32_t Bg, int32_t env_offset, int32_t* obs_dev, float* reward_dev,
+                           int32_t reward_cols, uint8_t* done_dev, int32_t done_cols, uint8_t* solved_dev,
+                           int32_t* num_unsatisfied_dev, int32_t* episode_step_dev, float* reward_host,
+                           uint8_t* done_host, uint8_t* solved_host, int32_t* num_unsatisfied_host,
+                           int32_t* episode_step_host, int32_t B, void* stream) {
+    if (!plan || !actions_host || !actions_dev || B < 0) return MSAT_EINVAL;
     cudaStream_t s = (cudaStream_t)stream;
     const Dims& d = plan->d;
     const size_t act_elems = (size_t)B * d.A * (d.action_mode == 0 ? 1 : d.V);
-    cudaError_t e = cudaMemcpyAsync(actions_dev, actions_host, act_elems * sizeof(int32_t), cudaMemcpyHostToDevice, s);
+    cudaError_t e = cudaSuccess;
+    if (act_elems)
+        e = cudaMemcpyAsync(actions_dev, actions_host, act_elems * sizeof(int32_t), cudaMemcpyHostToDevice, s);
     if (e != cudaSuccess) return (int)e;
-    int rc = msat_step(plan, bank, P, state, state, actions_dev, auto_reset, new_problem_idx, reset_keys, obs_dev,
-                       reward_dev, done_dev, done_cols, solved_dev, num_unsatisfied_dev, episode_step_dev, B, stream);
+    int rc = msat_rollout_step(plan, bank, P, state, state, actions_dev, rng_in, chain_out, Bg, env_offset, obs_dev,
+                               reward_dev, reward_cols, done_dev, done_cols, solved_dev, num_unsatisfied_dev,
+                               episode_step_dev, B, stream);
     if (rc != MSAT_OK) return rc;
-    if (reward_host && reward_dev)
-        e = cudaMemcpyAsync(reward_host, reward_dev, (size_t)B * d.A * sizeof(float), cudaMemcpyDeviceToHost, s);
-    if (e == cudaSuccess && done_host && done_dev)
-        e = cudaMemcpyAsync(done_host, done_dev, (size_t)B * done_cols, cudaMemcpyDeviceToHost, s);
-    if (e == cudaSuccess && solved_host && solved_dev)
-        e = cudaMemcpyAsync(solved_host, solved_dev, (size_t)B, cudaMemcpyDeviceToHost, s);
-    if (e == cudaSuccess && num_unsatisfied_host && num_unsatisfied_dev)
-        e = cudaMemcpyAsync(num_unsatisfied_host, num_unsatisfied_dev, (size_t)B * 4, cudaMemcpyDeviceToHost, s);
-    if (e == cudaSuccess && episode_step_host && episode_step_dev)
-        e = cudaMemcpyAsync(episode_step_host, episode_step_dev, (size_t)B * 4, cudaMemcpyDeviceToHost, s);
-    if (e != cudaSuccess) return (int)e;
+    if (B > 0) {
+        if (reward_host && reward_dev)
+            e = cudaMemcpyAsync(reward_host, reward_dev, (size_t)B * reward_cols * sizeof(float), cudaMemcpyDeviceToHost, s);
+        if (e == cudaSuccess && done_host && done_dev)
+            e = cudaMemcpyAsync(done_host, done_dev, (size_t)B * done_cols, cudaMemcpyDeviceToHost, s);
+        if (e == cudaSuccess && solved_host && solved_dev)
+            e = cudaMemcpyAsync(solved_host, solved_dev, (size_t)B, cudaMemcpyDeviceToHost, s);
+        if (e == cudaSuccess && num_unsatisfied_host && num_unsatisfied_dev)
+            e = cudaMemcpyAsync(num_unsatisfied_host, num_unsatisfied_dev, (size_t)B * 4, cudaMemcpyDeviceToHost, s);
+        if (e == cudaSuccess && episode_step_host && episode_step_dev)
+            e = cudaMemcpyAsync(episode_step_host, episode_step_dev, (size_t)B * 4, cudaMemcpyDeviceToHost, s);
+        if (e != cudaSuccess) return (int)e;
+    }
     return cuda_rc(cudaStreamSynchronize(s));
 }
 

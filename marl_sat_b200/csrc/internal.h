@@ -47,6 +47,7 @@ struct EnvArgs {
     int auto_reset;
     int32_t* obs;
     float* reward;
+    int reward_cols;
     uint8_t* done;
     int done_cols;
     uint8_t* solved;

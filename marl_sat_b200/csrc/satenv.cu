@@ -335,7 +335,8 @@ __global__ void __launch_bounds__(kCtaThreads) env_kernel(const Dims d, const En
         const bool done = solved || (step_old + 1 >= d.max_steps);        // env:258-259
         // pre-reset outputs stored in the Transition (learner:467-478)
         if (a.reward)
-            for (int i = gt; i < d.A; i += GS) a.reward[(size_t)e * d.A + i] = solved ? 1.0f : 0.0f;   // env:193
+            for (int i = gt; i < a.reward_cols; i += GS)
+                a.reward[(size_t)e * a.reward_cols + i] = solved ? 1.0f : 0.0f;                     // env:193
         if (a.done)
             for (int i = gt; i < a.done_cols; i += GS) a.done[(size_t)e * a.done_cols + i] = done ? 1 : 0;
         if (gt == 0) {

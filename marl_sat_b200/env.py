@@ -344,13 +344,15 @@ class SATEnv:
         raise TypeError("SATEnv.step() is unusable in the reference (reset needs problem_clauses); "
                         "call step_env(key, state, actions_array) or use marl_sat_b200.VecSATEnv")
 
-    def alloc_step_outputs(self, B: int, d=None, want_obs: bool = True) -> Dict[str, torch.Tensor]:
+    def alloc_step_outputs(self, B: int, d=None, want_obs: bool = True, compact: bool = False) -> Dict[str, torch.Tensor]:
+        """Device output buffers of one step.  ``compact=True`` keeps one reward / done column per env (the
+        shared team reward and ``done["__all__"]``) instead of one per agent."""
         dev = self._require_cuda()
         A, D = self.num_agents, self.obs_dim
         return {
             "obs": torch.empty((B, A, D), dtype=torch.int32, device=dev) if want_obs else None,
-            "reward": torch.empty((B, A), dtype=torch.float32, device=dev),
-            "done": torch.empty((B, A + 1), dtype=torch.uint8, device=dev),
+            "reward": torch.empty((B, 1 if compact else A), dtype=torch.float32, device=dev),
+            "done": torch.empty((B, 1 if compact else A + 1), dtype=torch.uint8, device=dev),
             "solved": torch.empty((B,), dtype=torch.uint8, device=dev),
             "num_unsatisfied": torch.empty((B,), dtype=torch.int32, device=dev),
             "episode_step": torch.empty((B,), dtype=torch.int32, device=dev),
@@ -361,12 +363,12 @@ class SATEnv:
                   new_problem_idx: Optional[torch.Tensor] = None, reset_keys: Optional[torch.Tensor] = None) -> None:
         """Thin call of ``msat_step`` on preallocated device tensors (enqueue only, graph-capturable)."""
         B = int(state_in.shape[0])
-        done = out.get("done")
+        done, reward = out.get("done"), out.get("reward")
         _lib.check(self._lib.msat_step(
             bank.plan.handle, _ptr(bank.data), bank.num_problems, _ptr(state_in), _ptr(state_out), _ptr(actions),
             1 if auto_reset else 0, _ptr(new_problem_idx), _ptr(reset_keys),
-            _ptr(out.get("obs")), _ptr(out.get("reward")), _ptr(done), int(done.shape[-1]) if done is not None else 0,
-            _ptr(out.get("solved")),
+            _ptr(out.get("obs")), _ptr(reward), int(reward.shape[-1]) if reward is not None else 0,
+            _ptr(done), int(done.shape[-1]) if done is not None else 0, _ptr(out.get("solved")),
             _ptr(out.get("num_unsatisfied")), _ptr(out.get("episode_step")), B, _stream_ptr(state_in.device)),
             "msat_step")
 

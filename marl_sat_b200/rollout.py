@@ -113,7 +113,8 @@ class VecSATEnv:
     """
 
     def __init__(self, env: SATEnv, problems: FormulaBank | torch.Tensor, num_envs: int, key,
-                 world_size: int = 1, rank: int = 0, emit_obs: bool = True, fused_keys: bool = True):
+                 world_size: int = 1, rank: int = 0, emit_obs: bool = True, fused_keys: bool = True,
+                 compact_outputs: bool = False):
         self.env = env
         self.fused_keys = fused_keys
         dev = env._require_cuda()
@@ -126,7 +127,7 @@ class VecSATEnv:
         self.state = torch.empty((B, d.state_words), dtype=torch.int32, device=dev)
         self.new_problem_idx = torch.empty((B,), dtype=torch.int32, device=dev)
         self.reset_keys = torch.empty((B, 2), dtype=torch.int32, device=dev)
-        self.out = env.alloc_step_outputs(B, d, want_obs=emit_obs)
+        self.out = env.alloc_step_outputs(B, d, want_obs=emit_obs, compact=compact_outputs)
         self._split_tmp = torch.empty(4, dtype=torch.int32, device=dev)
 
     # runner:289-295 -- key,_rng = split(key); idx = randint(_rng,...); reset_keys = split(_rng, B)
@@ -148,11 +149,12 @@ class VecSATEnv:
         out = self.out if out is None else out
         if self.fused_keys:
             # one launch: rng chain + per-env key derivation + step + auto-reset (msat_rollout_step)
-            done = out.get("done")
+            done, reward = out.get("done"), out.get("reward")
             _lib.check(self.env._lib.msat_rollout_step(
                 self.bank.plan.handle, _ptr(self.bank.data), self.bank.num_problems, _ptr(self.state),
                 _ptr(self.state), _ptr(actions), _ptr(self.keys.chain), _ptr(self.keys.next_chain),
-                self.num_envs_global, self.env_offset, _ptr(out.get("obs")), _ptr(out.get("reward")), _ptr(done),
+                self.num_envs_global, self.env_offset, _ptr(out.get("obs")), _ptr(reward),
+                int(reward.shape[-1]) if reward is not None else 0, _ptr(done),
                 int(done.shape[-1]) if done is not None else 0, _ptr(out.get("solved")),
                 _ptr(out.get("num_unsatisfied")), _ptr(out.get("episode_step")), self.num_envs,
                 _stream_ptr(self.state.device)), "msat_rollout_step")
@@ -166,38 +168,52 @@ class VecSATEnv:
         return out
 
     def alloc_host_io(self) -> Dict[str, torch.Tensor]:
-        """Pinned host buffers for ``step_host``: the action batch in, reward/done/info out."""
+        """Pinned host buffers for ``step_host``: the action batch in, reward/done/info out (same column
+        counts as the device outputs)."""
         env, B = self.env, self.num_envs
         act_shape = (B, env.num_agents) if env.action_mode == 0 else (B, env.num_agents, env.max_vars_per_agent)
         pin = dict(pin_memory=True)
         return {"actions": torch.zeros(act_shape, dtype=torch.int32, **pin),
-                "reward": torch.empty((B, env.num_agents), dtype=torch.float32, **pin),
-                "done": torch.empty((B, env.num_agents + 1), dtype=torch.uint8, **pin),
+                "reward": torch.empty(tuple(self.out["reward"].shape), dtype=torch.float32, **pin),
+                "done": torch.empty(tuple(self.out["done"].shape), dtype=torch.uint8, **pin),
                 "solved": torch.empty((B,), dtype=torch.uint8, **pin),
                 "num_unsatisfied": torch.empty((B,), dtype=torch.int32, **pin),
                 "episode_step": torch.empty((B,), dtype=torch.int32, **pin)}
 
     def step_host(self, host: Dict[str, torch.Tensor], actions_dev: Optional[torch.Tensor] = None) -> Dict[str, torch.Tensor]:
-        """End-to-end step for a host-side caller (``msat_step_host``): host actions are copied to the
-        device, the rollout step runs, reward/done/info are copied back and the stream is synchronised.
-        Observations stay in HBM (``self.out['obs']``) where the policy consumes them."""
+        """End-to-end rollout step for a host-side caller (``msat_rollout_step_host``): host actions are
+        copied to the device, the fused step runs, reward/done/info are copied back and the stream is
+        synchronised.  Observations stay in HBM (``self.out['obs']``) where the policy consumes them.
+        With ``compact_outputs`` the per-agent reward / done values (identical for all agents, env:196,260)
+        travel once per env; ``host_views`` expands them without copying."""
         out, dev = self.out, self.state.device
         if actions_dev is None:
             if not hasattr(self, "_actions_dev"):
                 self._actions_dev = torch.empty(host["actions"].shape, dtype=torch.int32, device=dev)
             actions_dev = self._actions_dev
-        self.keys.advance()
-        derive_env_keys(self.keys.prob_key, self.keys.reset_key, self.num_envs_global, self.env_offset, self.num_envs,
-                        self.bank.num_problems, self.new_problem_idx, self.reset_keys)
-        done = out["done"]
-        _lib.check(self.env._lib.msat_step_host(
+        done, reward = out["done"], out["reward"]
+        _lib.check(self.env._lib.msat_rollout_step_host(
             self.bank.plan.handle, _ptr(self.bank.data), self.bank.num_problems, _ptr(self.state),
-            _ptr(host["actions"]), _ptr(actions_dev), 1, _ptr(self.new_problem_idx), _ptr(self.reset_keys),
-            _ptr(out["obs"]), _ptr(out["reward"]), _ptr(done), int(done.shape[-1]), _ptr(out["solved"]),
-            _ptr(out["num_unsatisfied"]), _ptr(out["episode_step"]),
-            _ptr(host["reward"]), _ptr(host["done"]), _ptr(host["solved"]), _ptr(host["num_unsatisfied"]),
-            _ptr(host["episode_step"]), self.num_envs, _stream_ptr(dev)), "msat_step_host")
+            _ptr(host["actions"]), _ptr(actions_dev), _ptr(self.keys.chain), _ptr(self.keys.next_chain),
+            self.num_envs_global, self.env_offset, _ptr(out["obs"]), _ptr(reward), int(reward.shape[-1]),
+            _ptr(done), int(done.shape[-1]), _ptr(out["solved"]), _ptr(out["num_unsatisfied"]),
+            _ptr(out["episode_step"]), _ptr(host["reward"]), _ptr(host["done"]), _ptr(host["solved"]),
+            _ptr(host["num_unsatisfied"]), _ptr(host["episode_step"]), self.num_envs, _stream_ptr(dev)),
+            "msat_rollout_step_host")
+        self.keys.flip()
         return host
+
+    def host_views(self, host: Dict[str, torch.Tensor]):
+        """Reference-shaped dicts over the host buffers: rewards / dones keyed by agent (+ "__all__"),
+        as zero-copy views (every agent's value is the same scalar, env:196,260)."""
+        env = self.env
+        rew, done = host["reward"], host["done"].bool()
+        rewards = {a: rew[:, i if rew.shape[1] > 1 else 0] for i, a in enumerate(env.agents)}
+        dones = {a: done[:, i if done.shape[1] > 1 else 0] for i, a in enumerate(env.agents)}
+        dones["__all__"] = done[:, -1]
+        infos = {"solved": host["solved"].bool(), "num_unsatisfied": host["num_unsatisfied"],
+                 "episode_step": host["episode_step"]}
+        return rewards, dones, infos
 
     def sat_state(self) -> SATState:
         return SATState(self.env, self.bank, self.state, True)
@@ -217,7 +233,7 @@ class RolloutBuffer:
         self.env, self.bank, self.num_steps, self.num_envs = env, bank, T, B
         self.state = torch.empty((T, B, d.state_words), dtype=torch.int32, device=dev)     # pre-step state
         self.action = torch.empty(act_shape, dtype=torch.int32, device=dev)
-        self.reward = torch.empty((T, B, A), dtype=torch.float32, device=dev)
+        self.reward = torch.empty((T, B, 1), dtype=torch.float32, device=dev)                # team reward (agent 0)
         self.done = torch.empty((T, B, 1), dtype=torch.uint8, device=dev)                  # global_done only
         self.solved = torch.empty((T, B), dtype=torch.uint8, device=dev)
         self.num_unsatisfied = torch.empty((T, B), dtype=torch.int32, device=dev)

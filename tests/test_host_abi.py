@@ -74,7 +74,7 @@ def test_argument_errors_enqueue_nothing():
     env = M.SATEnv(20, 91, 8, verbose=False, device="cpu")
     plan = env._plan_for(3).handle
     assert lib.msat_reset(plan, None, 1, None, None, None, None, 4, None) == _lib.MSAT_EINVAL
-    assert lib.msat_step(plan, None, 1, None, None, None, 0, None, None, None, None, None, 0, None, None, None,
+    assert lib.msat_step(plan, None, 1, None, None, None, 0, None, None, None, None, 0, None, 0, None, None, None,
                          4, None) == _lib.MSAT_EINVAL
     assert lib.msat_env_keys(None, None, 8, 4, 8, 3, None, None, None) == _lib.MSAT_EINVAL   # shard exceeds batch
     assert lib.msat_gae(None, 1, 1, None, None, None, 0.9, 0.9, None, None, 4, 4, None) == _lib.MSAT_EINVAL

@@ -279,3 +279,38 @@ def test_full_size_properties_uf100_65536():
     _, st2, *_ = env.step_env(None, st1, acts)
     assert torch.equal(st2.variable_assignments, assign)
     assert int(st2.step.min()) == 2 and int(st2.step.max()) == 2
+
+
+def test_host_buffer_rollout_step_matches_oracle():
+    """msat_rollout_step_host (pinned host actions in, compact reward/done/info out) against the oracle."""
+    M = _msat()
+    n, m, B, P, max_steps = 20, 91, 40, 6, 2
+    problems = _formulas("uniform", P, n, m, 3, seed=21)
+    ref = SATEnvOracle(n, m, max_steps)
+    env = M.SATEnv(n, m, max_steps, verbose=False)
+    key0 = otf.prng_key(9)
+    vec = M.VecSATEnv(env, problems, B, key0, compact_outputs=True)
+    vec.reset()
+    key, idx0, rk0 = orollout.initial_reset_inputs(key0, B, P)
+    _, st_r = ref.reset(problems[idx0], rk0)
+    host = vec.alloc_host_io()
+    assert host["reward"].shape == (B, 1) and host["done"].shape == (B, 1) and host["actions"].is_pinned()
+    arng = np.random.default_rng(2)
+    for t in range(5):
+        acts = _random_actions(arng, ref, B)
+        ks = orollout.rollout_keys(key, B, P)
+        key = ks["rng"]
+        fo, st_r, rew_r, done_r, info_r = orollout.env_step_with_autoreset(
+            ref, st_r, acts, problems, ks["new_problem_indices"], ks["reset_keys"])
+        host["actions"].copy_(torch.from_numpy(acts))
+        vec.step_host(host)
+        rewards, dones, infos = vec.host_views(host)
+        for i, a in enumerate(env.agents):
+            assert np.array_equal(rewards[a].numpy(), rew_r[:, i])
+            assert np.array_equal(dones[a].numpy(), done_r)
+        assert np.array_equal(dones["__all__"].numpy(), done_r)
+        assert np.array_equal(infos["solved"].numpy(), info_r["solved"])
+        assert np.array_equal(infos["num_unsatisfied"].numpy(), info_r["num_unsatisfied"])
+        assert np.array_equal(infos["episode_step"].numpy(), info_r["episode_step"])
+        assert np.array_equal(to_np(vec.out["obs"]), fo)
+        assert_state_equal(vec.sat_state(), st_r, f"step {t} ")
