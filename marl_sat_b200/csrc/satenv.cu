@@ -301,6 +301,10 @@ __global__ void __launch_bounds__(kCtaThreads) env_kernel(const Dims d, const En
     }
     group_sync<GS>(gid);
 
+    // Every thread takes its copy of the scalar state fields NOW: thread 0 rewrites them in shared memory
+    // further down, and a warp that read `step` after that write would disagree with the others about
+    // `done` one step before the time-out and wait at a group barrier nobody else reaches.
+    const int step_old = (MODE == MODE_RESET) ? 0 : (int)st_tail[ST_STEP];
     int pidx;
     if (MODE == MODE_RESET) pidx = a.prob_idx[e];
     else pidx = (int)st_tail[ST_PIDX];
@@ -323,7 +327,6 @@ __global__ void __launch_bounds__(kCtaThreads) env_kernel(const Dims d, const En
     group_sync<GS>(gid);
     int nunsat = misc[0];
 
-    int step_old = (MODE == MODE_RESET) ? 0 : (int)st_tail[ST_STEP];
     if (MODE == MODE_STEP) {
         if (a.rng_in && blockIdx.x == 0 && threadIdx.x == 0) {
             // advance the rollout rng once per step (learner:397,416,426); chain_out never aliases rng_in

@@ -97,3 +97,40 @@ def test_empty_batch_is_a_no_op():
     adv, tgt = M.calculate_gae(torch.empty((0, 4), device="cuda"), torch.empty((0, 4), dtype=torch.uint8, device="cuda"),
                                torch.empty((0, 4), device="cuda"), torch.zeros(4, device="cuda"), 0.9, 0.9)
     assert adv.shape == (0, 4)
+
+
+@pytest.mark.timeout(300)
+@pytest.mark.parametrize("gs", [0, 64, 256])
+def test_timeout_boundary_stress(gs):
+    """Many envs, tiny max_steps: every env crosses the time-out boundary again and again, so every CTA
+    repeatedly takes the 'one step before time-out' and the reset path.  Regression test for a
+    shared-memory race on the step counter (a warp that re-read `step` after thread 0 had advanced it
+    disagreed about `done` and dead-locked the group barrier): all envs are checked with invariants, a
+    subset against the oracle."""
+    import marl_sat_b200 as M
+    from marl_sat_b200.synth import uniform_ksat
+    n, m, B, P, max_steps = 20, 91, 16384, 32, 3
+    problems = uniform_ksat(P, n, m, 3, seed=3)
+    ref = SATEnvOracle(n, m, max_steps)
+    env = M.SATEnv(n, m, max_steps, verbose=False, group_threads=gs)
+    key0 = otf.prng_key(123)
+    vec = M.VecSATEnv(env, problems, B, key0)
+    vec.reset()
+    key, idx0, rk0 = orollout.initial_reset_inputs(key0, B, P)
+    sub = np.arange(0, B, 67)
+    _, st_r = ref.reset(problems[idx0[sub]], rk0[sub])
+    g = torch.Generator(device="cuda").manual_seed(5)
+    for t in range(14):
+        acts = torch.randint(0, 5, (B, env.num_agents), generator=g, device="cuda", dtype=torch.int32)
+        out = vec.step(acts)
+        ks = orollout.rollout_keys(key, B, P)
+        key = ks["rng"]
+        fo, st_r, rew_r, done_r, info_r = orollout.env_step_with_autoreset(
+            ref, st_r, to_np(acts)[sub], problems, ks["new_problem_indices"][sub], ks["reset_keys"][sub])
+        es, done, solved = out["episode_step"], out["done"][:, -1].bool(), out["solved"].bool()
+        assert int(es.min()) >= 1 and int(es.max()) <= max_steps
+        assert torch.equal(done, solved | (es == max_steps))
+        assert np.array_equal(to_np(out["obs"])[sub], fo), f"step {t}"
+        assert np.array_equal(to_np(done)[sub], done_r)
+        assert np.array_equal(to_np(es)[sub], info_r["episode_step"])
+    torch.cuda.synchronize()
