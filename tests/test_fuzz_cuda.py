@@ -99,7 +99,7 @@ def test_empty_batch_is_a_no_op():
     assert adv.shape == (0, 4)
 
 
-@pytest.mark.timeout(300)
+@pytest.mark.timeout(300, method="thread")
 @pytest.mark.parametrize("gs", [0, 64, 256])
 def test_timeout_boundary_stress(gs):
     """Many envs, tiny max_steps: every env crosses the time-out boundary again and again, so every CTA

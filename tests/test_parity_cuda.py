@@ -314,3 +314,30 @@ def test_host_buffer_rollout_step_matches_oracle():
         assert np.array_equal(infos["episode_step"].numpy(), info_r["episode_step"])
         assert np.array_equal(to_np(vec.out["obs"]), fo)
         assert_state_equal(vec.sat_state(), st_r, f"step {t} ")
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_sharded_rollout_equals_single_device(world):
+    """Env sharding: `world` VecSATEnv shards, each deriving its keys from global env
+    indices, reproduce the single-device rollout exactly (no data-path collective needed)."""
+    M = _msat()
+    n, m, B, P, max_steps = 20, 91, 50, 7, 2
+    problems = _formulas("uniform", P, n, m, 3, seed=31)
+    env = M.SATEnv(n, m, max_steps, verbose=False)
+    bank = env.make_bank(problems)
+    key0 = otf.prng_key(77)
+    full = M.VecSATEnv(env, bank, B, key0)
+    shards = [M.VecSATEnv(env, bank, B, key0, world_size=world, rank=r) for r in range(world)]
+    obs_full = full.reset()
+    obs_sh = torch.cat([s.reset() for s in shards])
+    assert torch.equal(obs_full, obs_sh)
+    g = torch.Generator(device="cuda").manual_seed(1)
+    for t in range(6):
+        acts = torch.randint(0, 5, (B, env.num_agents), generator=g, device="cuda", dtype=torch.int32)
+        o = full.step(acts)
+        outs = [s.step(acts[s.env_offset:s.env_offset + s.num_envs].contiguous()) for s in shards]
+        for k_ in ("obs", "reward", "done", "solved", "num_unsatisfied", "episode_step"):
+            assert torch.equal(o[k_], torch.cat([x[k_] for x in outs])), (t, k_)
+        assert torch.equal(full.state, torch.cat([s.state for s in shards]))
+        for s in shards:
+            assert torch.equal(s.keys.chain, full.keys.chain)
