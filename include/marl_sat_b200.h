@@ -229,6 +229,15 @@ int msat_rollout_metrics(const float* reward, int64_t reward_stride_t, int64_t r
                          const int32_t* episode_step, int32_t num_steps, int32_t num_envs,
                          double* sums, void* stream);
 
+/* Per-variable flip gains and the greedy expert labels of the BC pre-training
+ * (src/runners/behavioral_cloning.py:54-100): delta_unsat int32[B,n] = change of the number of
+ * unsatisfied clauses if variable v alone were flipped (break - make); greedy_labels int32[B,A] = per
+ * agent the local index of its owned variable with the most negative delta (first wins ties) when that
+ * delta < tau, else the no-op action V.  Either output may be NULL. */
+int msat_flip_gains(const msat_plan* plan, const void* bank, int32_t num_problems,
+                    const uint32_t* state, int32_t num_envs, double tau,
+                    int32_t* delta_unsat, int32_t* greedy_labels, void* stream);
+
 /* Bookkeeping of the greedy evaluation loop (runner:57-70) after evaluation step t (0-based): envs
  * solved for the first time get ever_solved = 1, steps_to_solve = t+1 and solution int32[B,n] = their
  * assignment.  Initialise ever_solved = 0, steps_to_solve = max_steps, solution = 0 before step 0. */

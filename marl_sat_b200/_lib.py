@@ -55,6 +55,7 @@ SIGNATURES = {
     "msat_gnn_static": (C.c_int, [_p, _p, _i32, _p, _p, _p, _p]),
     "msat_gnn_dynamic": (C.c_int, [_p, _p, _i32, _p, _i32, _p, _p, _p]),
     "msat_rollout_metrics": (C.c_int, [_p, _i64, _i64, _p, _p, _p, _p, _i32, _i32, _p, _p]),
+    "msat_flip_gains": (C.c_int, [_p, _p, _i32, _p, _i32, _f64, _p, _p, _p]),
     "msat_eval_track": (C.c_int, [_p, _p, _p, _i32, _i32, _p, _p, _p, _p]),
 }
 

@@ -274,6 +274,14 @@ int msat_rollout_metrics(const float* reward, int64_t rs_t, int64_t rs_b, const 
                                           (cudaStream_t)stream));
 }
 
+int msat_flip_gains(const msat_plan* plan, const void* bank, int32_t P, const uint32_t* state, int32_t B, double tau,
+                    int32_t* delta_unsat, int32_t* greedy_labels, void* stream) {
+    if (!plan || B < 0 || P <= 0 || (B > 0 && (!bank || !state))) return MSAT_EINVAL;
+    if (plan->d.n * (int)sizeof(int) > 48 * 1024) return MSAT_EUNSUPPORTED;
+    return cuda_rc(launch_flip_gains(plan, static_cast<const uint8_t*>(bank), P, state, B, (float)tau, delta_unsat,
+                                     greedy_labels, (cudaStream_t)stream));
+}
+
 int msat_eval_track(const msat_plan* plan, const uint32_t* state, const uint8_t* solved, int32_t t, int32_t B,
                     uint8_t* ever_solved, int32_t* steps_to_solve, int32_t* solution, void* stream) {
     if (!plan || B < 0 || t < 0) return MSAT_EINVAL;

@@ -125,6 +125,71 @@ __global__ void __launch_bounds__(256) eval_track_kernel(const Dims d, const uin
     for (int v = 0; v < d.n; ++v) solution[(size_t)e * d.n + v] = (int)((st[v >> 5] >> (v & 31)) & 1u);
 }
 
+// ---- per-variable flip gains and the greedy expert labels (behavioral_cloning.py:54-100) -----------------
+// delta_unsat[v] = (#unsatisfied after flipping v alone) - (#unsatisfied now) = break[v] - make[v]:
+//   an unsatisfied clause becomes satisfied by flipping any variable it mentions (make, once per clause);
+//   a satisfied clause breaks iff all its true literals are on v and it has no false literal on v.
+// greedy label of agent a: the owned variable with the most negative delta (first wins ties), kept only
+// if that delta < tau, else the no-op action V.
+__global__ void __launch_bounds__(128) flip_gain_kernel(const Dims d, const uint8_t* __restrict__ bank, int P,
+                                                        const uint32_t* __restrict__ state, float tau,
+                                                        int32_t* __restrict__ delta_out, int32_t* __restrict__ labels) {
+    extern __shared__ int gain[];                     // [n] break - make
+    const int e = blockIdx.x, tid = threadIdx.x, nt = blockDim.x;
+    const uint32_t* st = state + (size_t)e * d.state_words;
+    int pidx = (int)st[d.aw + ST_PIDX];
+    pidx = pidx < 0 ? 0 : (pidx >= P ? P - 1 : pidx);
+    const uint16_t* lits = reinterpret_cast<const uint16_t*>(bank + (size_t)pidx * d.rec_bytes);
+    for (int v = tid; v < d.n; v += nt) gain[v] = 0;
+    __syncthreads();
+    for (int c = tid; c < d.m; c += nt) {
+        int ntrue = 0;
+        for (int j = 0; j < d.k; ++j) {
+            const uint32_t code = lits[lit_index(d.m, c, j)];
+            if (code != LIT_PAD) ntrue += (int)(((st[(code >> 1) >> 5] >> ((code >> 1) & 31)) ^ code) & 1u);
+        }
+        for (int j = 0; j < d.k; ++j) {
+            const uint32_t code = lits[lit_index(d.m, c, j)];
+            if (code == LIT_PAD) continue;
+            const uint32_t v = code >> 1;
+            bool first = true;              // handle each distinct variable of the clause once
+            int true_on_v = 0, false_on_v = 0;
+            for (int i = 0; i < d.k; ++i) {
+                const uint32_t ci = lits[lit_index(d.m, c, i)];
+                if (ci == LIT_PAD || (ci >> 1) != v) continue;
+                if (i < j) first = false;
+                const int t = (int)(((st[v >> 5] >> (v & 31)) ^ ci) & 1u);
+                true_on_v += t;
+                false_on_v += 1 - t;
+            }
+            if (!first) continue;
+            if (ntrue == 0) atomicSub(&gain[v], 1);                                   // make
+            else if (true_on_v == ntrue && false_on_v == 0) atomicAdd(&gain[v], 1);   // break
+        }
+    }
+    __syncthreads();
+    if (delta_out)
+        for (int v = tid; v < d.n; v += nt) delta_out[(size_t)e * d.n + v] = gain[v];
+    if (labels)
+        for (int a = tid; a < d.A; a += nt) {
+            const int start = group_start(d, a), size = group_size(d, a);
+            float best_delta = 0.0f;
+            int best = d.V;
+            for (int j = 0; j < size; ++j) {
+                const float dl = (float)gain[start + j];
+                if (dl < best_delta) { best_delta = dl; best = j; }
+            }
+            labels[(size_t)e * d.A + a] = (best_delta < tau) ? best : d.V;
+        }
+}
+
+cudaError_t launch_flip_gains(const msat_plan* plan, const uint8_t* bank, int P, const uint32_t* state, int B, float tau,
+                              int32_t* delta, int32_t* labels, cudaStream_t s) {
+    if (B == 0) return cudaSuccess;
+    flip_gain_kernel<<<B, 128, plan->d.n * sizeof(int), s>>>(plan->d, bank, P, state, tau, delta, labels);
+    return cudaGetLastError();
+}
+
 cudaError_t launch_gnn_static(const msat_plan* plan, const uint8_t* bank, int P, float* svf, float* a_pos,
                               float* a_neg, cudaStream_t s) {
     if (P == 0) return cudaSuccess;

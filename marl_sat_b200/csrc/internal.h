@@ -94,6 +94,8 @@ cudaError_t launch_gnn_dynamic(const msat_plan* plan, const uint8_t* bank, int P
 cudaError_t launch_rollout_metrics(const float* reward, long long rs_t, long long rs_b, const uint8_t* done,
                                    const uint8_t* solved, const int32_t* num_unsat, const int32_t* episode_step, int T,
                                    int B, double* sums, cudaStream_t s);
+cudaError_t launch_flip_gains(const msat_plan* plan, const uint8_t* bank, int P, const uint32_t* state, int B, float tau,
+                              int32_t* delta, int32_t* labels, cudaStream_t s);
 cudaError_t launch_eval_track(const msat_plan* plan, const uint32_t* state, const uint8_t* solved, int t, int B,
                               uint8_t* ever, int32_t* steps, int32_t* solution, cudaStream_t s);
 

@@ -78,3 +78,19 @@ def gnn_input_from_state(state: SATState, dense_adjacency: bool = False) -> GNNI
         gi = GNNInput(*[None if t is None else t[0] for t in
                         (gi.static_var_features, gi.assignment, gi.clause_features, gi.A_pos, gi.A_neg)])
     return gi
+
+
+def flip_gains(state: SATState, tau: float = 0.0):
+    """``(delta_unsat i32[B,n], greedy_labels i32[B,A])``: the change of ``num_unsatisfied`` if each
+    variable alone were flipped, and the per-agent greedy action labels of the BC expert
+    (``/root/reference/src/runners/behavioral_cloning.py:54-100``; ``tau`` = ``TAU_IMPROVE``)."""
+    lib = _lib.load()
+    bank, d, dev = state.bank, state.bank.plan.dims, state.packed.device
+    B = state.num_envs
+    delta = torch.empty((B, d.n), dtype=torch.int32, device=dev)
+    labels = torch.empty((B, d.A), dtype=torch.int32, device=dev)
+    _lib.check(lib.msat_flip_gains(bank.plan.handle, _ptr(bank.data), bank.num_problems, _ptr(state.packed), B,
+                                   float(tau), _ptr(delta), _ptr(labels), _stream_ptr(dev)), "msat_flip_gains")
+    if not state.batched:
+        return delta[0], labels[0]
+    return delta, labels

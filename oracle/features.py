@@ -73,3 +73,27 @@ def evaluate_policy(policy_fn, env: SATEnvOracle, clauses, keys, max_steps):
     solution = np.where(ever[:, None], assign_hist[first, np.arange(B)], 0)
     steps = np.where(ever, first + 1, max_steps)                           # runner:67
     return ever, steps.astype(np.int32), solution.astype(np.int32)
+
+
+def greedy_labels(env: SATEnvOracle, clauses: np.ndarray, assignments: np.ndarray, tau: float):
+    """``compute_joint_labels_parallel_greedy`` (behavioral_cloning.py:54-100) for ONE env, by brute force
+    like the reference: flip each owned variable, recompute the unsatisfied count.  Also returns the
+    per-variable deltas."""
+    cl = clauses[None]
+    _, base = env.calculate_satisfaction(assignments[None].astype(np.int32), cl)
+    deltas = np.zeros(env.num_vars, np.int32)
+    for v in range(env.num_vars):
+        tmp = assignments.copy()
+        tmp[v] ^= 1
+        _, new = env.calculate_satisfaction(tmp[None].astype(np.int32), cl)
+        deltas[v] = int(new[0]) - int(base[0])
+    labels = []
+    for i in range(env.num_agents):
+        valid = np.flatnonzero(env.action_mask[i])
+        best_delta, best = 0.0, env.max_vars_per_agent
+        for j, gv in enumerate(env.agent_vars[i][valid]):
+            delta = float(deltas[gv])
+            if delta < best_delta:
+                best_delta, best = delta, valid[j]
+        labels.append(best if best_delta < tau else env.max_vars_per_agent)
+    return np.array(labels, np.int32), deltas

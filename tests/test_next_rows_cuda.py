@@ -86,3 +86,21 @@ def test_greedy_evaluation_loop_matches_oracle():
     assert np.array_equal(to_np(steps_c), steps_r)
     assert np.array_equal(to_np(sol_c), sol_r)
     assert ever_r.any()
+
+
+@pytest.mark.parametrize("n,m,k,vpa,kind,tau", [(20, 91, 3, None, "uniform", 0.0), (35, 149, 3, 7, "uniform", -1.0),
+                                                (30, 60, 5, 4, "dups", 0.0), (50, 218, 7, 7, "mixed", 0.0)])
+def test_flip_gains_and_greedy_labels_match_brute_force(n, m, k, vpa, kind, tau):
+    B = 6
+    if kind == "dups":       # repeated variables, x and -x in one clause, zeros anywhere
+        M, _, keys, ref, env = _setup(n, m, 3, vpa, "uniform", B)
+        cl = np.random.default_rng(8).integers(-n, n + 1, size=(B, m, k)).astype(np.int32)
+    else:
+        M, cl, keys, ref, env = _setup(n, m, k, vpa, kind, B)
+    _, st_c = env.reset(cl, keys)
+    assign = to_np(st_c.variable_assignments)
+    delta, labels = M.flip_gains(st_c, tau=tau)
+    for b in range(B):
+        exp_labels, exp_delta = ofeat.greedy_labels(ref, cl[b], assign[b], tau)
+        assert np.array_equal(to_np(delta[b]), exp_delta), b
+        assert np.array_equal(to_np(labels[b]), exp_labels), b
