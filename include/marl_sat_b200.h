@@ -194,10 +194,13 @@ int msat_env_keys(const uint32_t* prob_key, const uint32_t* reset_key,
 /* Reverse GAE scan.  reward: float, element (t,b) at reward[t*reward_stride_t +
  * b*reward_stride_b] (a [T,B,A] buffer passes strides B*A and A: agent 0 is
  * read, learner:514; a dense team reward [T,B] passes B and 1).  done uint8[T,B],
- * value float[T,B], last_val float[B] -> advantages, targets float[T,B]. */
+ * value float[T,B], last_val float[B] -> advantages, targets float[T,B].
+ * stats (may be NULL): double[3] += {count, sum, sum of squares} of the advantages,
+ * accumulated by the scan itself so that the normalisation needs no separate pass
+ * (zero it first; not cleared by the call). */
 int msat_gae(const float* reward, int64_t reward_stride_t, int64_t reward_stride_b,
              const uint8_t* done, const float* value, const float* last_val,
-             double gamma, double gae_lambda, float* advantages, float* targets,
+             double gamma, double gae_lambda, float* advantages, float* targets, double* stats,
              int32_t num_steps, int32_t num_envs, void* stream);
 
 /* stats double[3] += {count, sum, sum of squares} over adv[0..count).  Zero it

@@ -232,12 +232,12 @@ int msat_env_keys(const uint32_t* prob_key, const uint32_t* reset_key, int32_t B
 }
 
 int msat_gae(const float* reward, int64_t rs_t, int64_t rs_b, const uint8_t* done, const float* value,
-             const float* last_val, double gamma, double gae_lambda, float* advantages, float* targets, int32_t T,
-             int32_t B, void* stream) {
+             const float* last_val, double gamma, double gae_lambda, float* advantages, float* targets, double* stats,
+             int32_t T, int32_t B, void* stream) {
     if (T < 0 || B < 0) return MSAT_EINVAL;
     if (T > 0 && B > 0 && (!reward || !done || !value || !last_val || !advantages || !targets)) return MSAT_EINVAL;
     return cuda_rc(launch_gae(reward, rs_t, rs_b, done, value, last_val, (float)gamma, (float)(gamma * gae_lambda),
-                              advantages, targets, T, B, (cudaStream_t)stream));
+                              advantages, targets, T, B, stats, (cudaStream_t)stream));
 }
 
 int msat_adv_stats(const float* adv, int64_t count, double* stats, void* stream) {

@@ -17,7 +17,8 @@ __device__ __forceinline__ void gae_segment(const float* __restrict__ reward, lo
                                             const uint8_t* __restrict__ done, const float* __restrict__ value,
                                             float gamma, float gl, float* __restrict__ adv,
                                             float* __restrict__ targets, int B, int b, int t0, int t1,
-                                            float next_value, float& gae, float& aprod) {
+                                            float next_value, float& gae, float& aprod, double& ssum,
+                                            double& ssq) {
     for (int t_hi = t1 - 1; t_hi >= t0; t_hi -= CH) {
         float r[CH], v[CH];
         uint8_t dn[CH];
@@ -39,6 +40,8 @@ __device__ __forceinline__ void gae_segment(const float* __restrict__ reward, lo
                 const float delta = __fsub_rn(__fadd_rn(r[i], __fmul_rn(__fmul_rn(gamma, next_value), nt)), v[i]);
                 gae = __fadd_rn(delta, __fmul_rn(c, gae));
                 if (WRITE) {
+                    ssum += (double)gae;
+                    ssq += (double)gae * (double)gae;
                     __stcs(adv + (size_t)t * B + b, gae);
                     __stcs(targets + (size_t)t * B + b, __fadd_rn(gae, v[i]));   // learner:526
                 } else {
@@ -60,7 +63,7 @@ __global__ void __launch_bounds__(32 * S) gae_kernel(const float* __restrict__ r
                                                      const float* __restrict__ value,
                                                      const float* __restrict__ last_val, float gamma, float gl,
                                                      float* __restrict__ adv, float* __restrict__ targets, int T,
-                                                     int B, int seg_len) {
+                                                     int B, int seg_len, double* __restrict__ stats) {
     __shared__ float sA[S][32], sB[S][32];
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const int b = blockIdx.x * 32 + lane;
@@ -69,11 +72,12 @@ __global__ void __launch_bounds__(32 * S) gae_kernel(const float* __restrict__ r
     float next_value = 0.0f;
     if (ok && t0 < t1) next_value = (t1 < T) ? __ldg(value + (size_t)t1 * B + b) : __ldg(last_val + b);
     float gae_in = 0.0f;
+    double ssum = 0.0, ssq = 0.0;      // fused advantage statistics (learner:530-531)
     if (S > 1) {
         float bsum = 0.0f, aprod = 1.0f;
         if (ok && t0 < t1)
             gae_segment<false, GAE_CHUNK>(reward, rs_t, rs_b, done, value, gamma, gl, adv, targets, B, b, t0, t1, next_value, bsum,
-                               aprod);
+                                          aprod, ssum, ssq);
         sA[w][lane] = aprod;
         sB[w][lane] = bsum;
         __syncthreads();
@@ -81,8 +85,19 @@ __global__ void __launch_bounds__(32 * S) gae_kernel(const float* __restrict__ r
     }
     float dummy = 1.0f;
     if (ok && t0 < t1)
-        gae_segment<true, (S == 1 ? GAE_CHUNK_1 : GAE_CHUNK)>(reward, rs_t, rs_b, done, value, gamma, gl, adv, targets, B, b, t0, t1, next_value, gae_in,
-                          dummy);
+        gae_segment<true, (S == 1 ? GAE_CHUNK_1 : GAE_CHUNK)>(reward, rs_t, rs_b, done, value, gamma, gl, adv, targets, B,
+                                                              b, t0, t1, next_value, gae_in, dummy, ssum, ssq);
+    if (stats) {       // one atomic pair per warp; the element count is added once
+        for (int o = 16; o > 0; o >>= 1) {
+            ssum += __shfl_xor_sync(0xffffffffu, ssum, o);
+            ssq += __shfl_xor_sync(0xffffffffu, ssq, o);
+        }
+        if (lane == 0) {
+            atomicAdd(&stats[1], ssum);
+            atomicAdd(&stats[2], ssq);
+            if (blockIdx.x == 0 && w == 0) atomicAdd(&stats[0], (double)T * (double)B);
+        }
+    }
 }
 
 __global__ void __launch_bounds__(256) adv_stats_kernel(const float* __restrict__ adv, long long count,
@@ -127,7 +142,7 @@ __global__ void __launch_bounds__(256) adv_normalize_kernel(float* __restrict__ 
 
 cudaError_t launch_gae(const float* reward, long long rs_t, long long rs_b, const uint8_t* done, const float* value,
                        const float* last_val, float gamma, float gl, float* adv, float* targets, int T, int B,
-                       cudaStream_t s) {
+                       double* stats, cudaStream_t s) {
     if (T == 0 || B == 0) return cudaSuccess;
     const int grid = (B + 31) / 32;
     // enough warps to cover HBM latency: >= 8 per SM, segments of at least one load chunk
@@ -136,7 +151,7 @@ cudaError_t launch_gae(const float* reward, long long rs_t, long long rs_b, cons
     const int seg_len = (T + S - 1) / S;
 #define MSAT_GAE_LAUNCH(SS)                                                                                         \
     gae_kernel<SS><<<grid, 32 * SS, 0, s>>>(reward, rs_t, rs_b, done, value, last_val, gamma, gl, adv, targets, T, B, \
-                                            seg_len)
+                                            seg_len, stats)
     switch (S) {
         case 1: MSAT_GAE_LAUNCH(1); break;
         case 2: MSAT_GAE_LAUNCH(2); break;

@@ -84,7 +84,7 @@ cudaError_t launch_env_keys(const uint32_t* prob_key, const uint32_t* reset_key,
                             int32_t* idx, uint32_t* keys, cudaStream_t s);
 cudaError_t launch_gae(const float* reward, long long rs_t, long long rs_b, const uint8_t* done, const float* value,
                        const float* last_val, float gamma, float gamma_lambda, float* adv, float* targets, int T, int B,
-                       cudaStream_t s);
+                       double* stats, cudaStream_t s);
 cudaError_t launch_adv_stats(const float* adv, long long count, double* stats, cudaStream_t s);
 cudaError_t launch_adv_normalize(float* adv, long long count, const double* stats, cudaStream_t s);
 cudaError_t launch_gnn_static(const msat_plan* plan, const uint8_t* bank, int P, float* svf, float* a_pos, float* a_neg,

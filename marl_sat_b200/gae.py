@@ -17,10 +17,11 @@ from .env import _ptr, _stream_ptr
 
 
 def calculate_gae(reward: torch.Tensor, done: torch.Tensor, value: torch.Tensor, last_val: torch.Tensor,
-                  gamma: float, gae_lambda: float) -> Tuple[torch.Tensor, torch.Tensor]:
+                  gamma: float, gae_lambda: float, stats: Optional[torch.Tensor] = None) -> Tuple[torch.Tensor, torch.Tensor]:
     """reward f32 ``[T,B,A]`` (agent 0 is read, learner:514) or ``[T,B]``; done bool/uint8 ``[T,B]``;
     value f32 ``[T,B]``; last_val f32 ``[B]`` -> ``(advantages, targets)`` f32 ``[T,B]``
-    (``targets = advantages + value`` with un-normalised advantages, learner:526)."""
+    (``targets = advantages + value`` with un-normalised advantages, learner:526).  ``stats`` (a zeroed
+    float64[3] device tensor) receives the advantages' (count, sum, sum of squares) from the same pass."""
     lib = _lib.load()
     if not reward.is_cuda:
         raise RuntimeError("calculate_gae needs CUDA tensors: there is no CPU fallback")
@@ -32,14 +33,12 @@ def calculate_gae(reward: torch.Tensor, done: torch.Tensor, value: torch.Tensor,
     done = done.contiguous()
     value = value.contiguous()
     last_val = last_val.contiguous()
-    if reward.dim() == 3:
-        rs_t, rs_b = reward.stride(0), reward.stride(1)
-    else:
-        rs_t, rs_b = reward.stride(0), reward.stride(1)
+    rs_t, rs_b = reward.stride(0), reward.stride(1)
     adv = torch.empty((T, B), dtype=torch.float32, device=value.device)
     tgt = torch.empty((T, B), dtype=torch.float32, device=value.device)
     _lib.check(lib.msat_gae(_ptr(reward), rs_t, rs_b, _ptr(done), _ptr(value), _ptr(last_val), float(gamma),
-                            float(gae_lambda), _ptr(adv), _ptr(tgt), T, B, _stream_ptr(value.device)), "msat_gae")
+                            float(gae_lambda), _ptr(adv), _ptr(tgt), _ptr(stats), T, B, _stream_ptr(value.device)),
+               "msat_gae")
     return adv, tgt
 
 
@@ -52,11 +51,13 @@ def advantage_stats(adv: torch.Tensor, stats: Optional[torch.Tensor] = None) -> 
     return stats
 
 
-def normalize_advantages(adv: torch.Tensor, group=None) -> torch.Tensor:
-    """In place ``adv = (adv - mean) / (std + 1e-8)`` with the global population std (learner:530-532)."""
+def normalize_advantages(adv: torch.Tensor, stats: Optional[torch.Tensor] = None, group=None) -> torch.Tensor:
+    """In place ``adv = (adv - mean) / (std + 1e-8)`` with the global population std (learner:530-532).
+    ``stats``: the local (count, sum, sum of squares) if ``calculate_gae`` already produced them (saves a
+    pass over ``adv``); with ``torch.distributed`` initialised they are all-reduced first (a private copy)."""
     lib = _lib.load()
     adv = adv if adv.is_contiguous() else adv.contiguous()
-    stats = advantage_stats(adv)
+    stats = advantage_stats(adv) if stats is None else stats.clone()
     if torch.distributed.is_available() and torch.distributed.is_initialized() and \
             torch.distributed.get_world_size(group) > 1:
         torch.distributed.all_reduce(stats, op=torch.distributed.ReduceOp.SUM, group=group)

@@ -77,7 +77,7 @@ def test_argument_errors_enqueue_nothing():
     assert lib.msat_step(plan, None, 1, None, None, None, 0, None, None, None, None, 0, None, 0, None, None, None,
                          4, None) == _lib.MSAT_EINVAL
     assert lib.msat_env_keys(None, None, 8, 4, 8, 3, None, None, None) == _lib.MSAT_EINVAL   # shard exceeds batch
-    assert lib.msat_gae(None, 1, 1, None, None, None, 0.9, 0.9, None, None, 4, 4, None) == _lib.MSAT_EINVAL
+    assert lib.msat_gae(None, 1, 1, None, None, None, 0.9, 0.9, None, None, None, 4, 4, None) == _lib.MSAT_EINVAL
     buf = (C.c_char * 4096)()
     addr = C.addressof(buf)
     mis = addr + 4 if (addr + 4) % 128 else addr + 8

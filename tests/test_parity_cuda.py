@@ -246,6 +246,16 @@ def test_gae_matches_oracle(T, B, A):
     norm_c = M.normalize_advantages(adv_c.clone())
     if T * B > 1:
         assert np.max(np.abs(to_np(norm_c) - norm_r)) <= 1e-5 * (np.abs(norm_r).max() + 1e-30) + 1e-6
+    # statistics fused into the scan give the same normalisation as the separate pass
+    stats = torch.zeros(3, dtype=torch.float64, device=dev)
+    adv_f, _ = M.calculate_gae(torch.from_numpy(reward).to(dev), torch.from_numpy(done).to(dev),
+                               torch.from_numpy(value).to(dev), torch.from_numpy(last_val).to(dev), 0.995, 0.95,
+                               stats=stats)
+    assert torch.equal(adv_f, adv_c)
+    ref_stats = M.advantage_stats(adv_c)
+    assert float(stats[0]) == T * B and torch.allclose(stats, ref_stats, rtol=1e-12, atol=1e-9)
+    if T * B > 1:
+        assert torch.allclose(M.normalize_advantages(adv_f.clone(), stats=stats), norm_c, rtol=1e-6, atol=1e-6)
 
 
 def test_full_size_properties_uf100_65536():
