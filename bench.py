@@ -11,8 +11,8 @@ info + auto-reset + observation kernel.  The global batch (65,536 envs for the h
 sharded across the N ranks in contiguous blocks with no collective on the step path; `value` is
 global env-steps/s from CUDA-event time, max over ranks.  Rank 0 prints ONE JSON line.
 
-`--impl reference` times the CPU restatement of the reference algorithm (oracle/, NumPy, one process
-per host core) on a bounded sample of the same workload: the reference's own JAX build cannot run here
+`--impl reference` times the CPU restatement of the reference algorithm (oracle/: plain C + OpenMP on all
+host cores; NumPy, one process per core, if gcc is missing) on a bounded sample of the same workload: the reference's own JAX build cannot run here
 (no JAX in the image), see DESIGN.md section 6.
 """
 from __future__ import annotations
@@ -95,7 +95,42 @@ def _cpu_worker(args):
     return time.perf_counter() - t0
 
 
+def run_cpu_restatement_c(wname, envs_per_core, steps, warmup):
+    """Compiled CPU baseline: the plain-C + OpenMP restatement (oracle/sat_env_c.c), all host cores."""
+    import numpy as np
+    from oracle import rollout as orollout
+    from oracle import threefry as otf
+    from oracle.c_port import SATEnvOracleC
+    w = WORKLOADS[wname]
+    cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    env = SATEnvOracleC(w["n"], w["m"], MAX_STEPS, vars_per_agent=w["vpa"])
+    env.set_threads(cores)              # torchrun exports OMP_NUM_THREADS=1 to every rank
+    threads = env.num_threads()
+    envs = envs_per_core * max(cores, 1)
+    problems = make_formulas(w, envs, 1000)
+    key, idx, rk = orollout.initial_reset_inputs(otf.prng_key(SEED), envs, envs)
+    st = env.reset(problems[idx], rk)
+    rng = np.random.default_rng(0)
+    acts = [rng.integers(0, env.V + 1, size=(envs, env.A)).astype(np.int32) for _ in range(4)]
+    t0 = 0.0
+    for i in range(warmup + steps):
+        if i == warmup:
+            t0 = time.perf_counter()
+        chain, nidx, keys = env.rollout_keys(key, envs, envs)
+        key = chain[:2].copy()
+        env.step(st, acts[i % 4], problems, nidx, keys)
+    t = time.perf_counter() - t0
+    return {"value": envs * steps / t, "unit": UNIT, "cores": threads, "kind": "port",
+            "sample": f"{wname}: {envs} envs x {steps} steps (+{warmup} warm-up) of the plain-C/OpenMP restatement "
+                      f"(oracle/sat_env_c.c: step all, reset all, select by done; learner:418-464) on {threads} "
+                      f"threads, {t:.2f} s"}, t
+
+
 def run_cpu_restatement(wname, envs_per_worker, steps, warmup):
+    try:
+        return run_cpu_restatement_c(wname, envs_per_worker, steps, warmup)
+    except Exception as e:      # no gcc / OpenMP: fall back to the NumPy restatement, one process per core
+        print(f"[bench] C restatement unavailable ({e!r}); timing the NumPy one", file=sys.stderr)
     import multiprocessing as mp
     cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
     ctx = mp.get_context("spawn")       # safe next to an initialised CUDA context; workers import NumPy only
@@ -123,13 +158,13 @@ def main_reference(args):
         "impl": "reference", "metric": METRIC, "value": base["value"], "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t / max(1, args.steps),
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "int32", "data": "synthetic",
-        "config": {"workload": f"{wname} (n={w['n']}, m={w['m']}, k={w['k']}), bounded sample of "
-                               f"{envs_per_worker * cores} envs per step on {cores} host cores",
+        "config": {"workload": f"{wname} (n={w['n']}, m={w['m']}, k={w['k']}), bounded sample per step on "
+                               f"{cores} host threads: {base['sample']}",
                    "max_steps": MAX_STEPS, "auto_reset": True},
         "cpu_baseline": base,
         "e2e": {"value": base["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "note": "CPU restatement of the reference algorithm (oracle/, NumPy); the reference's JAX build is not "
-                "installable in this image (no jax wheel, no network)",
+        "note": "CPU restatement of the reference algorithm (oracle/: plain C + OpenMP, NumPy fallback); the "
+                "reference's JAX build is not installable in this image (no jax wheel, no network)",
     }
     print(json.dumps(line))
     return 0
