@@ -2,6 +2,7 @@
 // validation and kernel enqueue.  No allocation, no synchronisation (except msat_step_host, which is
 // documented to synchronise), no torch types.
 #include <math.h>
+#include <mutex>
 #include <new>
 
 #include "../../include/marl_sat_b200.h"
@@ -14,6 +15,28 @@ namespace {
 inline bool aligned(const void* p, size_t a) { return (reinterpret_cast<uintptr_t>(p) & (a - 1)) == 0; }
 inline int cuda_rc(cudaError_t e) { return e == cudaSuccess ? MSAT_OK : (int)e; }
 constexpr int kMaxSmem = 227 * 1024;
+
+// Two internal streams + fork/join events used by msat_rollout_step_host to overlap PCIe copies with the
+// kernel; created lazily for the current device (one process drives one GPU in this design).
+struct HostPipe {
+    std::mutex mu;
+    int dev = -1;
+    cudaStream_t ws[2] = {nullptr, nullptr};
+    cudaEvent_t fork = nullptr, join[2] = {nullptr, nullptr};
+    cudaError_t init() {
+        int cur = 0;
+        cudaError_t e = cudaGetDevice(&cur);
+        if (e != cudaSuccess || cur == dev) return e;
+        for (int w = 0; w < 2 && e == cudaSuccess; ++w) {
+            e = cudaStreamCreateWithFlags(&ws[w], cudaStreamNonBlocking);
+            if (e == cudaSuccess) e = cudaEventCreateWithFlags(&join[w], cudaEventDisableTiming);
+        }
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&fork, cudaEventDisableTiming);
+        if (e == cudaSuccess) dev = cur;
+        return e;
+    }
+};
+HostPipe g_pipe;
 
 }  // namespace
 
@@ -187,26 +210,66 @@ int msat_rollout_step_host(const msat_plan* plan, const void* bank, int32_t P, u
     if (!plan || !actions_host || !actions_dev || B < 0) return MSAT_EINVAL;
     cudaStream_t s = (cudaStream_t)stream;
     const Dims& d = plan->d;
-    const size_t act_elems = (size_t)B * d.A * (d.action_mode == 0 ? 1 : d.V);
-    cudaError_t e = cudaSuccess;
-    if (act_elems)
-        e = cudaMemcpyAsync(actions_dev, actions_host, act_elems * sizeof(int32_t), cudaMemcpyHostToDevice, s);
-    if (e != cudaSuccess) return (int)e;
-    int rc = msat_rollout_step(plan, bank, P, state, state, actions_dev, rng_in, chain_out, Bg, env_offset, obs_dev,
-                               reward_dev, reward_cols, done_dev, done_cols, solved_dev, num_unsatisfied_dev,
-                               episode_step_dev, B, stream);
-    if (rc != MSAT_OK) return rc;
-    if (B > 0) {
+    const size_t act_per_env = (size_t)d.A * (d.action_mode == 0 ? 1 : d.V);
+    const size_t obs_per_env = (size_t)d.A * d.D;
+
+    // One slice [b0, b0 + bc) of the batch on stream `w`: actions in, fused step, results out.
+    auto run_slice = [&](int b0, int bc, cudaStream_t w) -> int {
+        cudaError_t e = cudaSuccess;
+        if (bc > 0 && act_per_env)
+            e = cudaMemcpyAsync(actions_dev + b0 * act_per_env, actions_host + b0 * act_per_env,
+                                (size_t)bc * act_per_env * sizeof(int32_t), cudaMemcpyHostToDevice, w);
+        if (e != cudaSuccess) return (int)e;
+        uint32_t* st = state + (size_t)b0 * d.state_words;
+        int rc = msat_rollout_step(plan, bank, P, st, st, actions_dev + b0 * act_per_env, rng_in, chain_out, Bg,
+                                   env_offset + b0, obs_dev ? obs_dev + b0 * obs_per_env : nullptr,
+                                   reward_dev ? reward_dev + (size_t)b0 * reward_cols : nullptr, reward_cols,
+                                   done_dev ? done_dev + (size_t)b0 * done_cols : nullptr, done_cols,
+                                   solved_dev ? solved_dev + b0 : nullptr,
+                                   num_unsatisfied_dev ? num_unsatisfied_dev + b0 : nullptr,
+                                   episode_step_dev ? episode_step_dev + b0 : nullptr, bc, (void*)w);
+        if (rc != MSAT_OK || bc == 0) return rc;
         if (reward_host && reward_dev)
-            e = cudaMemcpyAsync(reward_host, reward_dev, (size_t)B * reward_cols * sizeof(float), cudaMemcpyDeviceToHost, s);
+            e = cudaMemcpyAsync(reward_host + (size_t)b0 * reward_cols, reward_dev + (size_t)b0 * reward_cols,
+                                (size_t)bc * reward_cols * sizeof(float), cudaMemcpyDeviceToHost, w);
         if (e == cudaSuccess && done_host && done_dev)
-            e = cudaMemcpyAsync(done_host, done_dev, (size_t)B * done_cols, cudaMemcpyDeviceToHost, s);
+            e = cudaMemcpyAsync(done_host + (size_t)b0 * done_cols, done_dev + (size_t)b0 * done_cols,
+                                (size_t)bc * done_cols, cudaMemcpyDeviceToHost, w);
         if (e == cudaSuccess && solved_host && solved_dev)
-            e = cudaMemcpyAsync(solved_host, solved_dev, (size_t)B, cudaMemcpyDeviceToHost, s);
+            e = cudaMemcpyAsync(solved_host + b0, solved_dev + b0, (size_t)bc, cudaMemcpyDeviceToHost, w);
         if (e == cudaSuccess && num_unsatisfied_host && num_unsatisfied_dev)
-            e = cudaMemcpyAsync(num_unsatisfied_host, num_unsatisfied_dev, (size_t)B * 4, cudaMemcpyDeviceToHost, s);
+            e = cudaMemcpyAsync(num_unsatisfied_host + b0, num_unsatisfied_dev + b0, (size_t)bc * 4,
+                                cudaMemcpyDeviceToHost, w);
         if (e == cudaSuccess && episode_step_host && episode_step_dev)
-            e = cudaMemcpyAsync(episode_step_host, episode_step_dev, (size_t)B * 4, cudaMemcpyDeviceToHost, s);
+            e = cudaMemcpyAsync(episode_step_host + b0, episode_step_dev + b0, (size_t)bc * 4, cudaMemcpyDeviceToHost, w);
+        return (int)e;
+    };
+
+    constexpr int kSlices = 4;
+    if (B < 4096) {   // small batch: one slice on the caller's stream
+        int rc = run_slice(0, B, s);
+        if (rc != MSAT_OK) return rc;
+        return cuda_rc(cudaStreamSynchronize(s));
+    }
+    // Large batch: slices alternate between two internal streams so that the action upload of slice
+    // i+1 and the result download of slice i-1 overlap the kernel of slice i (separate copy engines).
+    {
+        std::lock_guard<std::mutex> lock(g_pipe.mu);
+        cudaError_t e = g_pipe.init();
+        if (e != cudaSuccess) return (int)e;
+        e = cudaEventRecord(g_pipe.fork, s);
+        for (int w = 0; w < 2 && e == cudaSuccess; ++w) e = cudaStreamWaitEvent(g_pipe.ws[w], g_pipe.fork, 0);
+        if (e != cudaSuccess) return (int)e;
+        const int per = (((B + kSlices - 1) / kSlices) + 63) & ~63;   // multiple of 64 envs keeps every slice aligned
+        for (int c = 0, b0 = 0; b0 < B; ++c, b0 += per) {
+            const int bc = B - b0 < per ? B - b0 : per;
+            int rc = run_slice(b0, bc, g_pipe.ws[c & 1]);
+            if (rc != MSAT_OK) return rc;
+        }
+        for (int w = 0; w < 2 && e == cudaSuccess; ++w) {
+            e = cudaEventRecord(g_pipe.join[w], g_pipe.ws[w]);
+            if (e == cudaSuccess) e = cudaStreamWaitEvent(s, g_pipe.join[w], 0);
+        }
         if (e != cudaSuccess) return (int)e;
     }
     return cuda_rc(cudaStreamSynchronize(s));

@@ -351,3 +351,31 @@ def test_sharded_rollout_equals_single_device(world):
         assert torch.equal(full.state, torch.cat([s.state for s in shards]))
         for s in shards:
             assert torch.equal(s.keys.chain, full.keys.chain)
+
+
+def test_host_step_sliced_pipeline_equals_device_step():
+    """Large batches take the sliced two-stream path of msat_rollout_step_host; it must produce exactly the
+    outputs, state and rng chain of the single-launch device step (odd batch size: ragged last slice)."""
+    M = _msat()
+    n, m, B, P, max_steps = 20, 91, 9001, 16, 3
+    problems = _formulas("uniform", P, n, m, 3, seed=41)
+    env = M.SATEnv(n, m, max_steps, verbose=False)
+    bank = env.make_bank(problems)
+    key0 = otf.prng_key(5)
+    dev_vec = M.VecSATEnv(env, bank, B, key0, compact_outputs=True)
+    host_vec = M.VecSATEnv(env, bank, B, key0, compact_outputs=True)
+    assert torch.equal(dev_vec.reset(), host_vec.reset())
+    host = host_vec.alloc_host_io()
+    g = torch.Generator(device="cuda").manual_seed(3)
+    for t in range(7):
+        acts = torch.randint(0, 5, (B, env.num_agents), generator=g, device="cuda", dtype=torch.int32)
+        out = dev_vec.step(acts)
+        host["actions"].copy_(acts.cpu())
+        host_vec.step_host(host)
+        torch.cuda.synchronize()
+        for k_ in ("reward", "done", "solved", "num_unsatisfied", "episode_step"):
+            assert torch.equal(host[k_], out[k_].cpu()), (t, k_)
+            assert torch.equal(host_vec.out[k_], out[k_]), (t, k_)
+        assert torch.equal(host_vec.out["obs"], out["obs"])
+        assert torch.equal(host_vec.state, dev_vec.state)
+        assert torch.equal(host_vec.keys.chain, dev_vec.keys.chain)
