@@ -199,8 +199,42 @@ class ClockSampler:
             self.ok = True
         except Exception as e:          # pragma: no cover
             self.err = repr(e)
+            self._init_smi(torch_device_index)
+
+    # fallback when NVML's Python binding is unusable: poll nvidia-smi (the recipe's clocks line)
+    def _init_smi(self, index):     # pragma: no cover
+        import shutil
+        import subprocess
+        if not shutil.which("nvidia-smi"):
+            return
+        try:
+            import torch
+            uuid = str(torch.cuda.get_device_properties(index).uuid)
+            sel = uuid if uuid.startswith("GPU-") else "GPU-" + uuid
+            q = subprocess.run(["nvidia-smi", "-i", sel, "--query-gpu=clocks.max.sm", "--format=csv,noheader,nounits"],
+                               capture_output=True, text=True, timeout=20)
+            self.max_mhz = int(q.stdout.strip().splitlines()[0])
+            self._smi = subprocess.Popen(
+                ["nvidia-smi", "-i", sel, "--query-gpu=clocks.sm,clocks_event_reasons.active",
+                 "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE, text=True)
+            self.nv = None
+            self.ok = True
+        except Exception as e:
+            self.err += " / nvidia-smi: " + repr(e)
+
+    def _loop_smi(self):            # pragma: no cover
+        for line in self._smi.stdout:
+            if self._stop.is_set():
+                break
+            try:
+                mhz, reasons = [x.strip() for x in line.split(",")[:2]]
+                self.samples.append((time.perf_counter(), int(mhz), int(reasons, 16)))
+            except Exception:
+                pass
 
     def _loop(self):
+        if self.nv is None:
+            return self._loop_smi()
         nv = self.nv
         while not self._stop.is_set():
             try:
@@ -222,6 +256,8 @@ class ClockSampler:
     def stop(self):
         if self._thread:
             self._stop.set()
+            if getattr(self, "_smi", None) is not None:
+                self._smi.terminate()
             self._thread.join(timeout=2)
 
     def summary(self, t0, t1):
