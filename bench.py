@@ -307,8 +307,13 @@ def main_ours(args):
     env = M.SATEnv(w["n"], w["m"], MAX_STEPS, vars_per_agent=w["vpa"], verbose=False, device=dev,
                    group_threads=args.group_threads)
     P = args.problems or Bg
-    problems = torch.from_numpy(make_formulas(w, P, 20261018 + 2))
-    bank = env.make_bank(problems)
+    # synthetic formulas are drawn on the device (same distribution as the NumPy generator the tests use)
+    from marl_sat_b200 import synth
+    if w["kind"] == "mixed":
+        problems = synth.mixed_ksat_torch(P, w["n"], w["m"], 3, w["k"], seed=20261018 + 2, device=dev)
+    else:
+        problems = synth.uniform_ksat_torch(P, w["n"], w["m"], w["k"], seed=20261018 + 2, device=dev)
+    bank = env.make_bank(problems, validate=False)
     del problems
     vec = M.VecSATEnv(env, bank, Bg, M.prng_key(SEED), world_size=shard_world, rank=shard_rank)
     B = vec.num_envs

@@ -250,6 +250,16 @@ int msat_eval_track(const msat_plan* plan, const uint32_t* state, const uint8_t*
                     int32_t num_envs, uint8_t* ever_solved, int32_t* steps_to_solve, int32_t* solution,
                     void* stream);
 
+/* Native DIMACS CNF reader (host only; replaces parse_cnf, src/utils/data_parser.py:8-42).  Parses `len`
+ * bytes of `text`.  Call once with clauses == NULL to obtain clause_count (rows actually present) and
+ * max_width (longest clause, terminating 0 excluded), then again with clauses int32[clause_count,
+ * clause_stride] (clause_stride >= max_width) to receive the literals, 0-padded on the right.  num_vars /
+ * num_clauses are the header's values (either may be NULL).  strict != 0 reproduces the reference exactly
+ * (a blank line is an empty clause, a '%' footer is an error); strict == 0 skips blank lines and stops at '%'.
+ * Returns MSAT_EINVAL for a malformed token or header. */
+int msat_dimacs_parse(const char* text, size_t len, int32_t strict, int32_t* num_vars, int32_t* num_clauses,
+                      int32_t* clause_count, int32_t* max_width, int32_t* clauses, int32_t clause_stride);
+
 #ifdef __cplusplus
 }
 #endif

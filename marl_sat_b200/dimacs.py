@@ -37,6 +37,40 @@ def parse_cnf(file_path: str, strict: bool = False) -> Tuple[int, int, List[List
     return num_vars, num_clauses, clauses
 
 
+def parse_cnf_native(file_path: str, strict: bool = False) -> Tuple[int, int, np.ndarray]:
+    """``parse_cnf`` through the native reader of the shared library (``msat_dimacs_parse``): returns
+    ``(num_vars, num_clauses, clauses int32[rows, max_width])`` with narrower clauses 0-padded."""
+    import ctypes as C
+
+    from . import _lib
+    lib = _lib.load()
+    with open(file_path, "rb") as f:
+        text = f.read()
+    nv, nc, rows, width = C.c_int32(), C.c_int32(), C.c_int32(), C.c_int32()
+    _lib.check(lib.msat_dimacs_parse(text, len(text), 1 if strict else 0, C.byref(nv), C.byref(nc), C.byref(rows),
+                                     C.byref(width), None, 0), f"msat_dimacs_parse({file_path})")
+    out = np.zeros((rows.value, max(width.value, 1)), dtype=np.int32)
+    _lib.check(lib.msat_dimacs_parse(text, len(text), 1 if strict else 0, None, None, C.byref(rows), C.byref(width),
+                                     out.ctypes.data_as(C.c_void_p), out.shape[1]), f"msat_dimacs_parse({file_path})")
+    return nv.value, nc.value, out[:, :width.value] if width.value else out[:, :0]
+
+
+def load_cnf_bank_array(cnf_data_dir: str, strict: bool = False) -> np.ndarray:
+    """All ``*.cnf`` files of a directory (sorted, like data_parser.py:60) as one ``int32[P, m, k]`` array via the
+    native reader; files must share the clause count, narrower files are 0-padded to the widest clause."""
+    names = sorted(f for f in os.listdir(cnf_data_dir) if f.endswith(".cnf"))
+    arrays = [parse_cnf_native(os.path.join(cnf_data_dir, n), strict=strict)[2] for n in names]
+    if not arrays:
+        return np.zeros((0, 0, 0), np.int32)
+    if len({a.shape[0] for a in arrays}) != 1:
+        raise ValueError("problems have different clause counts")
+    k = max(a.shape[1] for a in arrays)
+    out = np.zeros((len(arrays), arrays[0].shape[0], k), np.int32)
+    for i, a in enumerate(arrays):
+        out[i, :, :a.shape[1]] = a
+    return out
+
+
 def load_cnf_problems(cnf_data_dir: str, strict: bool = False) -> List[Dict]:
     names = sorted(f for f in os.listdir(cnf_data_dir) if f.endswith(".cnf"))
     problems = []

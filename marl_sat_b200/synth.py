@@ -35,3 +35,35 @@ def mixed_ksat(num_formulas: int, n: int, m: int, kmin: int = 3, kmax: int = 7, 
     width = rng.integers(kmin, kmax + 1, size=(num_formulas, m, 1))
     keep = np.arange(kmax)[None, None, :] < width
     return np.where(keep, full, 0).astype(np.int32)
+
+
+def uniform_ksat_torch(num_formulas: int, n: int, m: int, k: int = 3, seed: int = 0, device="cpu"):
+    """Same distribution as ``uniform_ksat`` generated with torch on ``device`` (bench set-up of tens of
+    thousands of formulas in milliseconds on the GPU).  Deterministic per (seed, device type); the values
+    differ from the NumPy generator's."""
+    import torch
+    if k > n:
+        raise ValueError("k distinct variables need k <= n")
+    g = torch.Generator(device=device).manual_seed(seed)
+    vars_ = torch.randint(0, n, (num_formulas, m, k), generator=g, device=device, dtype=torch.int32)
+    while True:   # re-draw rows with a repeated variable
+        dup = torch.zeros((num_formulas, m), dtype=torch.bool, device=device)
+        for i in range(k):
+            for j in range(i + 1, k):
+                dup |= vars_[:, :, i] == vars_[:, :, j]
+        cnt = int(dup.sum())
+        if cnt == 0:
+            break
+        vars_[dup] = torch.randint(0, n, (cnt, k), generator=g, device=device, dtype=torch.int32)
+    neg = torch.randint(0, 2, vars_.shape, generator=g, device=device, dtype=torch.int32).bool()
+    lits = vars_ + 1
+    return torch.where(neg, -lits, lits)
+
+
+def mixed_ksat_torch(num_formulas: int, n: int, m: int, kmin: int = 3, kmax: int = 7, seed: int = 0, device="cpu"):
+    import torch
+    full = uniform_ksat_torch(num_formulas, n, m, kmax, seed=seed + 1, device=device)
+    g = torch.Generator(device=device).manual_seed(seed)
+    width = torch.randint(kmin, kmax + 1, (num_formulas, m, 1), generator=g, device=device)
+    keep = torch.arange(kmax, device=device)[None, None, :] < width
+    return torch.where(keep, full, torch.zeros_like(full))
