@@ -33,9 +33,9 @@ def main():
     a = ap.parse_args()
 
     if a.cnf_dir:
-        probs = [p for p in dimacs.load_cnf_problems(a.cnf_dir)
+        probs = [p for p in dimacs.load_cnf_problems(a.cnf_dir)         # Python reader (reference semantics)
                  if p["num_vars"] == a.num_vars and p["num_clauses"] == a.num_clauses]
-        clauses = dimacs.stack_problems(probs)
+        clauses = dimacs.stack_problems(probs)                          # dimacs.load_cnf_bank_array = native reader
     else:
         clauses = uniform_ksat(256, a.num_vars, a.num_clauses, 3, seed=a.seed)
     env = M.SATEnv(a.num_vars, a.num_clauses, a.max_steps, vars_per_agent=a.vars_per_agent)
