@@ -154,36 +154,34 @@ class SATState:
 
     def _leaf(self, name: str) -> torch.Tensor:
         if name not in self._cache:
-            self._export()
+            self._export(name)
         t = self._cache[name]
         return t if self.batched else t[0]
 
-    def _export(self) -> None:
+    # leaf -> (shape builder, dtype); exported one at a time so that reading `step` does not
+    # materialise the [B, A, m] masks
+    _EXPORT_ORDER = ("variable_assignments", "clauses_satisfied_status", "num_unsatisfied", "step", "done", "clauses",
+                     "agent_clause_masks", "agent_neighbor_masks", "literal_to_agent_idx", "problem_idx")
+
+    def _export(self, name: str) -> None:
         env, d = self.env, self.bank.plan.dims
         B, dev = self.num_envs, self.packed.device
-        i32 = dict(dtype=torch.int32, device=dev)
-        u8 = dict(dtype=torch.uint8, device=dev)
-        out = {
-            "variable_assignments": torch.empty((B, d.n), **i32),
-            "clauses_satisfied_status": torch.empty((B, d.m), **u8),
-            "num_unsatisfied": torch.empty((B,), **i32),
-            "step": torch.empty((B,), **i32),
-            "done": torch.empty((B, d.A), **u8),
-            "clauses": torch.empty((B, d.m, d.k), **i32),
-            "agent_clause_masks": torch.empty((B, d.A, d.m), **i32),
-            "agent_neighbor_masks": torch.empty((B, d.A, d.n), **i32),
-            "literal_to_agent_idx": torch.empty((B, d.m, d.k), **i32),
-            "problem_idx": torch.empty((B,), **i32),
+        shapes = {
+            "variable_assignments": ((B, d.n), torch.int32), "clauses_satisfied_status": ((B, d.m), torch.uint8),
+            "num_unsatisfied": ((B,), torch.int32), "step": ((B,), torch.int32), "done": ((B, d.A), torch.uint8),
+            "clauses": ((B, d.m, d.k), torch.int32), "agent_clause_masks": ((B, d.A, d.m), torch.int32),
+            "agent_neighbor_masks": ((B, d.A, d.n), torch.int32), "literal_to_agent_idx": ((B, d.m, d.k), torch.int32),
+            "problem_idx": ((B,), torch.int32),
         }
+        shape, dtype = shapes[name]
+        out = torch.empty(shape, dtype=dtype, device=dev)
+        ptrs = [_ptr(out) if leaf == name else None for leaf in self._EXPORT_ORDER]
         _lib.check(env._lib.msat_export_state(
-            self.bank.plan.handle, _ptr(self.bank.data), self.bank.num_problems, _ptr(self.packed), B,
-            *[_ptr(out[k]) for k in ("variable_assignments", "clauses_satisfied_status", "num_unsatisfied", "step",
-                                     "done", "clauses", "agent_clause_masks", "agent_neighbor_masks",
-                                     "literal_to_agent_idx", "problem_idx")],
+            self.bank.plan.handle, _ptr(self.bank.data), self.bank.num_problems, _ptr(self.packed), B, *ptrs,
             _stream_ptr(dev)), "msat_export_state")
-        out["clauses_satisfied_status"] = out["clauses_satisfied_status"].bool()
-        out["done"] = out["done"].bool()
-        self._cache = out
+        if name in ("clauses_satisfied_status", "done"):
+            out = out.bool()
+        self._cache[name] = out
 
 
 def _make_leaf_property(name):
