@@ -146,6 +146,8 @@ class VecSATEnv:
         """One rollout step (learner:397-464) for this shard.  ``actions`` int32 ``[B, A]`` (mode 0) or
         ``[B, A, V]`` (mode 1) on the device.  Returns the output dict (obs of the state to continue
         from; reward/done/info are the pre-reset values, learner:467-478)."""
+        if out is None and self.fused_keys:
+            return self._step_fast(actions)
         out = self.out if out is None else out
         if self.fused_keys:
             # one launch: rng chain + per-env key derivation + step + auto-reset (msat_rollout_step)
@@ -166,6 +168,30 @@ class VecSATEnv:
         self.env.step_into(self.bank, self.state, self.state, actions, out, auto_reset=True,
                            new_problem_idx=self.new_problem_idx, reset_keys=self.reset_keys)
         return out
+
+    def _step_fast(self, actions: torch.Tensor) -> Dict[str, torch.Tensor]:
+        """``step`` on the env's own output buffers with every constant argument bound once: at small
+        per-GPU batches the ~80 µs kernel is short enough for per-call Python work to matter."""
+        args = getattr(self, "_fast_args", None)
+        if args is None or args[-1] is not self.out["obs"]:
+            out, k = self.out, self.keys
+            done, reward = out["done"], out["reward"]
+            fixed = [self.bank.plan.handle, _ptr(self.bank.data), self.bank.num_problems, _ptr(self.state),
+                     _ptr(self.state), None, None, None, self.num_envs_global, self.env_offset, _ptr(out["obs"]),
+                     _ptr(reward), int(reward.shape[-1]), _ptr(done), int(done.shape[-1]), _ptr(out["solved"]),
+                     _ptr(out["num_unsatisfied"]), _ptr(out["episode_step"]), self.num_envs, None]
+            chains = (_ptr(k._bufs[0]), _ptr(k._bufs[1]))
+            args = self._fast_args = (fixed, chains, self.env._lib.msat_rollout_step, out["obs"])
+        fixed, chains, fn, _ = args
+        cur = self.keys._cur
+        fixed[5] = actions.data_ptr()
+        fixed[6], fixed[7] = chains[cur], chains[1 - cur]
+        fixed[19] = torch.cuda.current_stream(self.state.device).cuda_stream
+        rc = fn(*fixed)
+        if rc != 0:
+            _lib.check(rc, "msat_rollout_step")
+        self.keys._cur = 1 - cur
+        return self.out
 
     def alloc_host_io(self) -> Dict[str, torch.Tensor]:
         """Pinned host buffers for ``step_host``: the action batch in, reward/done/info out (same column
