@@ -155,8 +155,9 @@ int msat_export_state(const msat_plan* plan, const void* bank, int32_t num_probl
 /* Host-buffer entry point of one rollout step (msat_rollout_step) for callers that keep actions and
  * results in (pinned) host memory: copies `actions_host` to `actions_dev`, runs the fused step
  * (rng chain + key derivation + step + auto-reset), copies reward / done / solved / num_unsatisfied /
- * episode_step back into the `*_host` buffers (each may be NULL) and synchronises the stream.  Batches
- * of 4096+ envs are processed as four slices alternating between two internal streams so that the PCIe
+ * episode_step back into the `*_host` buffers (each may be NULL) and synchronises the stream.  Result
+ * buffers that are adjacent in both address spaces are copied as one transfer; batches of 32768+ envs
+ * are processed as four slices alternating between two internal streams so that the PCIe
  * copies overlap the kernel.  All device workspaces are caller-owned; observations stay on the device
  * (obs_dev). */
 int msat_rollout_step_host(const msat_plan* plan, const void* bank, int32_t num_problems,

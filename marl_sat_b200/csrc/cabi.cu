@@ -229,24 +229,31 @@ int msat_rollout_step_host(const msat_plan* plan, const void* bank, int32_t P, u
                                    num_unsatisfied_dev ? num_unsatisfied_dev + b0 : nullptr,
                                    episode_step_dev ? episode_step_dev + b0 : nullptr, bc, (void*)w);
         if (rc != MSAT_OK || bc == 0) return rc;
-        if (reward_host && reward_dev)
-            e = cudaMemcpyAsync(reward_host + (size_t)b0 * reward_cols, reward_dev + (size_t)b0 * reward_cols,
-                                (size_t)bc * reward_cols * sizeof(float), cudaMemcpyDeviceToHost, w);
-        if (e == cudaSuccess && done_host && done_dev)
-            e = cudaMemcpyAsync(done_host + (size_t)b0 * done_cols, done_dev + (size_t)b0 * done_cols,
-                                (size_t)bc * done_cols, cudaMemcpyDeviceToHost, w);
-        if (e == cudaSuccess && solved_host && solved_dev)
-            e = cudaMemcpyAsync(solved_host + b0, solved_dev + b0, (size_t)bc, cudaMemcpyDeviceToHost, w);
-        if (e == cudaSuccess && num_unsatisfied_host && num_unsatisfied_dev)
-            e = cudaMemcpyAsync(num_unsatisfied_host + b0, num_unsatisfied_dev + b0, (size_t)bc * 4,
-                                cudaMemcpyDeviceToHost, w);
-        if (e == cudaSuccess && episode_step_host && episode_step_dev)
-            e = cudaMemcpyAsync(episode_step_host + b0, episode_step_dev + b0, (size_t)bc * 4, cudaMemcpyDeviceToHost, w);
+        // device->host result copies; outputs that are adjacent in both address spaces (the Python layer
+        // carves them out of one device block and one pinned block) travel as ONE copy
+        struct Seg { const char* dev; char* host; size_t bytes; };
+        Seg seg[5];
+        int ns = 0;
+        auto add = [&](const void* dv, void* hs, size_t off, size_t bytes) {
+            if (dv && hs && bytes) seg[ns++] = Seg{static_cast<const char*>(dv) + off, static_cast<char*>(hs) + off, bytes};
+        };
+        add(reward_dev, reward_host, (size_t)b0 * reward_cols * sizeof(float), (size_t)bc * reward_cols * sizeof(float));
+        add(num_unsatisfied_dev, num_unsatisfied_host, (size_t)b0 * 4, (size_t)bc * 4);
+        add(episode_step_dev, episode_step_host, (size_t)b0 * 4, (size_t)bc * 4);
+        add(done_dev, done_host, (size_t)b0 * done_cols, (size_t)bc * done_cols);
+        add(solved_dev, solved_host, (size_t)b0, (size_t)bc);
+        for (int i = 1; i < ns; ++i)          // insertion sort by device address
+            for (int j = i; j > 0 && seg[j].dev < seg[j - 1].dev; --j) { Seg t = seg[j]; seg[j] = seg[j - 1]; seg[j - 1] = t; }
+        for (int i = 0; i < ns && e == cudaSuccess;) {
+            Seg cur = seg[i++];
+            while (i < ns && seg[i].dev == cur.dev + cur.bytes && seg[i].host == cur.host + cur.bytes) cur.bytes += seg[i++].bytes;
+            e = cudaMemcpyAsync(cur.host, cur.dev, cur.bytes, cudaMemcpyDeviceToHost, w);
+        }
         return (int)e;
     };
 
     constexpr int kSlices = 4;
-    if (B < 4096) {   // small batch: one slice on the caller's stream
+    if (B < 32768) {   // one slice on the caller's stream (slicing only pays when the kernel is long)
         int rc = run_slice(0, B, s);
         if (rc != MSAT_OK) return rc;
         return cuda_rc(cudaStreamSynchronize(s));

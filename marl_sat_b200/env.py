@@ -342,18 +342,30 @@ class SATEnv:
         raise TypeError("SATEnv.step() is unusable in the reference (reset needs problem_clauses); "
                         "call step_env(key, state, actions_array) or use marl_sat_b200.VecSATEnv")
 
-    def alloc_step_outputs(self, B: int, d=None, want_obs: bool = True, compact: bool = False) -> Dict[str, torch.Tensor]:
-        """Device output buffers of one step.  ``compact=True`` keeps one reward / done column per env (the
-        shared team reward and ``done["__all__"]``) instead of one per agent."""
-        dev = self._require_cuda()
+    def alloc_step_outputs(self, B: int, d=None, want_obs: bool = True, compact: bool = False,
+                           pinned_host: bool = False) -> Dict[str, torch.Tensor]:
+        """Output buffers of one step.  ``compact=True`` keeps one reward / done column per env (the shared
+        team reward and ``done["__all__"]``) instead of one per agent.  reward, num_unsatisfied,
+        episode_step, done and solved are views of ONE block (in that order, 4-byte fields first) so that a
+        host mirror allocated with ``pinned_host=True`` receives them in a single transfer."""
         A, D = self.num_agents, self.obs_dim
+        rc, dc = (1, 1) if compact else (A, A + 1)
+        if pinned_host:
+            block = torch.empty(B * (4 * rc + 8 + dc + 1), dtype=torch.uint8, pin_memory=True)
+            obs = None
+        else:
+            dev = self._require_cuda()
+            block = torch.empty(B * (4 * rc + 8 + dc + 1), dtype=torch.uint8, device=dev)
+            obs = torch.empty((B, A, D), dtype=torch.int32, device=dev) if want_obs else None
+        o0, o1, o2, o3 = 4 * rc * B, 4 * rc * B + 4 * B, 4 * rc * B + 8 * B, 4 * rc * B + 8 * B + dc * B
         return {
-            "obs": torch.empty((B, A, D), dtype=torch.int32, device=dev) if want_obs else None,
-            "reward": torch.empty((B, 1 if compact else A), dtype=torch.float32, device=dev),
-            "done": torch.empty((B, 1 if compact else A + 1), dtype=torch.uint8, device=dev),
-            "solved": torch.empty((B,), dtype=torch.uint8, device=dev),
-            "num_unsatisfied": torch.empty((B,), dtype=torch.int32, device=dev),
-            "episode_step": torch.empty((B,), dtype=torch.int32, device=dev),
+            "obs": obs,
+            "reward": block[:o0].view(torch.float32).view(B, rc),
+            "num_unsatisfied": block[o0:o1].view(torch.int32),
+            "episode_step": block[o1:o2].view(torch.int32),
+            "done": block[o2:o3].view(B, dc),
+            "solved": block[o3:],
+            "_block": block,
         }
 
     def step_into(self, bank: FormulaBank, state_in: torch.Tensor, state_out: torch.Tensor, actions: torch.Tensor,

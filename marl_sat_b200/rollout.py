@@ -198,13 +198,9 @@ class VecSATEnv:
         counts as the device outputs)."""
         env, B = self.env, self.num_envs
         act_shape = (B, env.num_agents) if env.action_mode == 0 else (B, env.num_agents, env.max_vars_per_agent)
-        pin = dict(pin_memory=True)
-        return {"actions": torch.zeros(act_shape, dtype=torch.int32, **pin),
-                "reward": torch.empty(tuple(self.out["reward"].shape), dtype=torch.float32, **pin),
-                "done": torch.empty(tuple(self.out["done"].shape), dtype=torch.uint8, **pin),
-                "solved": torch.empty((B,), dtype=torch.uint8, **pin),
-                "num_unsatisfied": torch.empty((B,), dtype=torch.int32, **pin),
-                "episode_step": torch.empty((B,), dtype=torch.int32, **pin)}
+        host = env.alloc_step_outputs(B, compact=self.out["reward"].shape[-1] == 1, pinned_host=True)
+        host["actions"] = torch.zeros(act_shape, dtype=torch.int32, pin_memory=True)
+        return host
 
     def step_host(self, host: Dict[str, torch.Tensor], actions_dev: Optional[torch.Tensor] = None) -> Dict[str, torch.Tensor]:
         """End-to-end rollout step for a host-side caller (``msat_rollout_step_host``): host actions are

@@ -353,11 +353,13 @@ def test_sharded_rollout_equals_single_device(world):
             assert torch.equal(s.keys.chain, full.keys.chain)
 
 
-def test_host_step_sliced_pipeline_equals_device_step():
-    """Large batches take the sliced two-stream path of msat_rollout_step_host; it must produce exactly the
-    outputs, state and rng chain of the single-launch device step (odd batch size: ragged last slice)."""
+@pytest.mark.parametrize("B", [9001, 33001], ids=["single-slice", "four-slices-two-streams"])
+def test_host_step_sliced_pipeline_equals_device_step(B):
+    """msat_rollout_step_host (coalesced result copy; batches >= 32768 envs sliced over two internal streams)
+    must produce exactly the outputs, state and rng chain of the single-launch device step (odd batch sizes:
+    ragged last slice)."""
     M = _msat()
-    n, m, B, P, max_steps = 20, 91, 9001, 16, 3
+    n, m, P, max_steps = 20, 91, 16, 3
     problems = _formulas("uniform", P, n, m, 3, seed=41)
     env = M.SATEnv(n, m, max_steps, verbose=False)
     bank = env.make_bank(problems)
