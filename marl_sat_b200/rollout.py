@@ -213,29 +213,43 @@ class VecSATEnv:
             if not hasattr(self, "_actions_dev"):
                 self._actions_dev = torch.empty(host["actions"].shape, dtype=torch.int32, device=dev)
             actions_dev = self._actions_dev
-        done, reward = out["done"], out["reward"]
-        _lib.check(self.env._lib.msat_rollout_step_host(
-            self.bank.plan.handle, _ptr(self.bank.data), self.bank.num_problems, _ptr(self.state),
-            _ptr(host["actions"]), _ptr(actions_dev), _ptr(self.keys.chain), _ptr(self.keys.next_chain),
-            self.num_envs_global, self.env_offset, _ptr(out["obs"]), _ptr(reward), int(reward.shape[-1]),
-            _ptr(done), int(done.shape[-1]), _ptr(out["solved"]), _ptr(out["num_unsatisfied"]),
-            _ptr(out["episode_step"]), _ptr(host["reward"]), _ptr(host["done"]), _ptr(host["solved"]),
-            _ptr(host["num_unsatisfied"]), _ptr(host["episode_step"]), self.num_envs, _stream_ptr(dev)),
-            "msat_rollout_step_host")
-        self.keys.flip()
+        bound = getattr(self, "_host_args", None)
+        if bound is None or bound[2] is not host["reward"] or bound[3] is not out["obs"]:
+            done, reward, k = out["done"], out["reward"], self.keys
+            fixed = [self.bank.plan.handle, _ptr(self.bank.data), self.bank.num_problems, _ptr(self.state),
+                     None, None, None, None, self.num_envs_global, self.env_offset, _ptr(out["obs"]), _ptr(reward),
+                     int(reward.shape[-1]), _ptr(done), int(done.shape[-1]), _ptr(out["solved"]),
+                     _ptr(out["num_unsatisfied"]), _ptr(out["episode_step"]), _ptr(host["reward"]), _ptr(host["done"]),
+                     _ptr(host["solved"]), _ptr(host["num_unsatisfied"]), _ptr(host["episode_step"]), self.num_envs,
+                     None]
+            bound = self._host_args = (fixed, (_ptr(k._bufs[0]), _ptr(k._bufs[1])), host["reward"], out["obs"])
+        fixed, chains = bound[0], bound[1]
+        cur = self.keys._cur
+        fixed[4], fixed[5] = host["actions"].data_ptr(), actions_dev.data_ptr()
+        fixed[6], fixed[7] = chains[cur], chains[1 - cur]
+        fixed[24] = torch.cuda.current_stream(dev).cuda_stream
+        rc = self.env._lib.msat_rollout_step_host(*fixed)
+        if rc != 0:
+            _lib.check(rc, "msat_rollout_step_host")
+        self.keys._cur = 1 - cur
         return host
 
     def host_views(self, host: Dict[str, torch.Tensor]):
         """Reference-shaped dicts over the host buffers: rewards / dones keyed by agent (+ "__all__"),
-        as zero-copy views (every agent's value is the same scalar, env:196,260)."""
+        as zero-copy views (every agent's value is the same scalar, env:196,260).  The views alias the
+        persistent pinned buffers, so they are built once and stay valid across steps."""
+        cached = getattr(self, "_host_views", None)
+        if cached is not None and cached[0] is host["reward"]:
+            return cached[1]
         env = self.env
-        rew, done = host["reward"], host["done"].bool()
+        rew, done = host["reward"], host["done"].view(torch.bool)
         rewards = {a: rew[:, i if rew.shape[1] > 1 else 0] for i, a in enumerate(env.agents)}
         dones = {a: done[:, i if done.shape[1] > 1 else 0] for i, a in enumerate(env.agents)}
         dones["__all__"] = done[:, -1]
-        infos = {"solved": host["solved"].bool(), "num_unsatisfied": host["num_unsatisfied"],
+        infos = {"solved": host["solved"].view(torch.bool), "num_unsatisfied": host["num_unsatisfied"],
                  "episode_step": host["episode_step"]}
-        return rewards, dones, infos
+        self._host_views = (host["reward"], (rewards, dones, infos))
+        return self._host_views[1]
 
     def sat_state(self) -> SATState:
         return SATState(self.env, self.bank, self.state, True)
