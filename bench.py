@@ -471,6 +471,35 @@ def main_ours(args):
                             "one in-place map (8 B)"}
         del g_reward, g_done, g_value, g_last, adv, tgt
 
+    # ---- extra: the reference policy's actual input ----------------------
+    # its networks read the GNN input, never the local observations, so a GNN-style consumer can skip the
+    # 63 KB/env observation write: rollout step without obs + per-step dynamic GNN features.  Reported as an
+    # extra key only; the headline metric above always includes the observations.
+    gnn_info = None
+    if world == 1 and not args.no_gnn_leg:
+        from marl_sat_b200.features import dynamic_features, static_graph
+        vec_g = M.VecSATEnv(env, bank, Bg, M.prng_key(SEED + 2), emit_obs=False, compact_outputs=True)
+        vec_g.reset()
+        static_graph(bank)                      # per-formula part, once
+        for i in range(5):
+            vec_g.step(actions[i])
+            dynamic_features(vec_g.sat_state())
+        torch.cuda.synchronize()
+        q0, q1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        Kg = min(K, 100)
+        q0.record()
+        for i in range(Kg):
+            vec_g.step(actions[i % ACTION_CYCLE])
+            assign, cf = dynamic_features(vec_g.sat_state())
+        q1.record()
+        torch.cuda.synchronize()
+        g_ms = q0.elapsed_time(q1) / Kg
+        gnn_info = {"value": Bg / (g_ms * 1e-3), "unit": UNIT, "ms_per_step": g_ms, "steps": Kg,
+                    "bytes_out_per_env_step": 4 * w["n"] + 12 * w["m"],
+                    "what": "msat_rollout_step without local observations + msat_gnn_dynamic (assignment int32[B,n], "
+                            "clause_features float32[B,m,3]); static graph features emitted once per formula bank"}
+        del vec_g, assign, cf
+
     # ---- reduce over ranks (max time) ------------------------------------------------------------------
     t = torch.tensor([ms, kernel_ms, e2e_ms, e2e_obs[0] if e2e_obs else 0.0], dtype=torch.float64, device=dev)
     if world > 1:
@@ -522,6 +551,8 @@ def main_ours(args):
             line["e2e_obs_to_host"] = {"value": Bg * args.e2e_obs_steps / (e2e_obs_ms * 1e-3), "unit": UNIT,
                                        "d2h_bytes_per_step": (d2h + e2e_obs[1]) * world, "steps": args.e2e_obs_steps,
                                        "what": "as e2e, plus the int32 observations copied to pinned host memory"}
+        if gnn_info:
+            line["gnn_input_mode"] = gnn_info
         if gae_info:
             gae_info["scan_frac_of_hbm_peak"] = gae_info["scan_gbs"] / peak
             line["gae"] = gae_info
@@ -551,6 +582,7 @@ def parse_args(argv=None):
     ap.add_argument("--cpu-envs-per-core", type=int, default=128)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-gae", action="store_true")
+    ap.add_argument("--no-gnn-leg", action="store_true")
     ap.add_argument("--graph", type=int, default=0, metavar="G",
                     help="replay the rollout steps as CUDA graphs of G steps each (0 = plain launches)")
     ap.add_argument("--gae-steps", type=int, default=512, help="T of the GAE leg (configs/MAPPO_CONFIG.yaml NUM_STEPS)")
