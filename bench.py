@@ -477,28 +477,28 @@ def main_ours(args):
     # extra key only; the headline metric above always includes the observations.
     gnn_info = None
     if world == 1 and not args.no_gnn_leg:
-        from marl_sat_b200.features import dynamic_features, static_graph
-        vec_g = M.VecSATEnv(env, bank, Bg, M.prng_key(SEED + 2), emit_obs=False, compact_outputs=True)
+        from marl_sat_b200.features import static_graph
+        vec_g = M.VecSATEnv(env, bank, Bg, M.prng_key(SEED + 2), emit_obs=False, compact_outputs=True,
+                            gnn_outputs=True)
         vec_g.reset()
         static_graph(bank)                      # per-formula part, once
         for i in range(5):
             vec_g.step(actions[i])
-            dynamic_features(vec_g.sat_state())
         torch.cuda.synchronize()
         q0, q1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         Kg = min(K, 100)
         q0.record()
         for i in range(Kg):
             vec_g.step(actions[i % ACTION_CYCLE])
-            assign, cf = dynamic_features(vec_g.sat_state())
         q1.record()
         torch.cuda.synchronize()
         g_ms = q0.elapsed_time(q1) / Kg
         gnn_info = {"value": Bg / (g_ms * 1e-3), "unit": UNIT, "ms_per_step": g_ms, "steps": Kg,
                     "bytes_out_per_env_step": 4 * w["n"] + 12 * w["m"],
-                    "what": "msat_rollout_step without local observations + msat_gnn_dynamic (assignment int32[B,n], "
-                            "clause_features float32[B,m,3]); static graph features emitted once per formula bank"}
-        del vec_g, assign, cf
+                    "what": "msat_rollout_step_gnn: one launch per step, no local observations, dynamic GNN input "
+                            "(assignment int32[B,n], clause_features float32[B,m,3]) emitted from the staged formula "
+                            "record; static graph features emitted once per formula bank"}
+        del vec_g
 
     # ---- reduce over ranks (max time) ------------------------------------------------------------------
     t = torch.tensor([ms, kernel_ms, e2e_ms, e2e_obs[0] if e2e_obs else 0.0], dtype=torch.float64, device=dev)

@@ -135,6 +135,20 @@ int msat_rollout_step(const msat_plan* plan, const void* bank, int32_t num_probl
                       uint8_t* solved, int32_t* num_unsatisfied, int32_t* episode_step,
                       int32_t num_envs, void* stream);
 
+/* msat_rollout_step for a GNN-style consumer (the reference's actor/critic read the GNN input, never the
+ * local observations): same step, but instead of obs int32[B,A,D] it emits the dynamic
+ * part of the GNN input of the state the caller continues from -- assignment int32[B,n] and
+ * clause_features float[B,m,3] = {is_sat, #true literals / 3.0, 1} (learner:165-195) -- straight from the
+ * staged formula record.  Either may be NULL.  The static part comes from msat_gnn_static once per bank. */
+int msat_rollout_step_gnn(const msat_plan* plan, const void* bank, int32_t num_problems,
+                          const uint32_t* state_in, uint32_t* state_out, const int32_t* actions,
+                          const uint32_t* rng_in, uint32_t* chain_out,
+                          int32_t num_envs_global, int32_t env_offset,
+                          int32_t* assignment, float* clause_features,
+                          float* reward, int32_t reward_cols, uint8_t* done, int32_t done_cols,
+                          uint8_t* solved, int32_t* num_unsatisfied, int32_t* episode_step,
+                          int32_t num_envs, void* stream);
+
 /* Replaces `SATEnv.get_obs(state)` (env:345-398): obs int32[B,A,D] from a state. */
 int msat_get_obs(const msat_plan* plan, const void* bank, int32_t num_problems,
                  const uint32_t* state, int32_t* obs, int32_t num_envs, void* stream);

@@ -43,6 +43,7 @@ SIGNATURES = {
     "msat_reset": (C.c_int, [_p, _p, _i32, _p, _p, _p, _p, _i32, _p]),
     "msat_step": (C.c_int, [_p, _p, _i32, _p, _p, _p, _i32, _p, _p, _p, _p, _i32, _p, _i32, _p, _p, _p, _i32, _p]),
     "msat_rollout_step": (C.c_int, [_p, _p, _i32, _p, _p, _p, _p, _p, _i32, _i32, _p, _p, _i32, _p, _i32, _p, _p, _p, _i32, _p]),
+    "msat_rollout_step_gnn": (C.c_int, [_p, _p, _i32, _p, _p, _p, _p, _p, _i32, _i32, _p, _p, _p, _i32, _p, _i32, _p, _p, _p, _i32, _p]),
     "msat_get_obs": (C.c_int, [_p, _p, _i32, _p, _p, _i32, _p]),
     "msat_export_state": (C.c_int, [_p, _p, _i32, _p, _i32] + [_p] * 10 + [_p]),
     "msat_rollout_step_host": (C.c_int, [_p, _p, _i32, _p, _p, _p, _p, _p, _i32, _i32, _p, _p, _i32, _p, _i32, _p, _p, _p] + [_p] * 5 + [_i32, _p]),

@@ -174,6 +174,31 @@ int msat_rollout_step(const msat_plan* plan, const void* bank, int32_t P, const 
     return cuda_rc(launch_env(plan, MODE_STEP, a, (cudaStream_t)stream));
 }
 
+int msat_rollout_step_gnn(const msat_plan* plan, const void* bank, int32_t P, const uint32_t* state_in,
+                          uint32_t* state_out, const int32_t* actions, const uint32_t* rng_in, uint32_t* chain_out,
+                          int32_t Bg, int32_t env_offset, int32_t* assignment, float* clause_features, float* reward,
+                          int32_t reward_cols, uint8_t* done, int32_t done_cols, uint8_t* solved,
+                          int32_t* num_unsatisfied, int32_t* episode_step, int32_t B, void* stream) {
+    if (!plan || B < 0 || P <= 0 || (done && done_cols <= 0) || (reward && reward_cols <= 0)) return MSAT_EINVAL;
+    if (!rng_in || !chain_out || Bg <= 0 || env_offset < 0 || (long long)env_offset + B > Bg) return MSAT_EINVAL;
+    if (Bg > (1 << 30)) return MSAT_EUNSUPPORTED;
+    {
+        const uintptr_t r = reinterpret_cast<uintptr_t>(rng_in), c = reinterpret_cast<uintptr_t>(chain_out);
+        if (r + 8 > c && c + 40 > r) return MSAT_EINVAL;
+    }
+    if (B > 0 && (!bank || !state_in || !state_out || !actions)) return MSAT_EINVAL;
+    if (!aligned(bank, 128) || !aligned(state_in, 16) || !aligned(state_out, 16)) return MSAT_EALIGN;
+    EnvArgs a{};
+    a.bank = static_cast<const uint8_t*>(bank); a.P = P;
+    a.state_in = state_in; a.state_out = state_out; a.actions = actions;
+    a.auto_reset = 1; a.rng_in = rng_in; a.chain_out = chain_out; a.Bg = (uint32_t)Bg; a.env_off = (uint32_t)env_offset;
+    a.gnn_assign = assignment; a.gnn_cf = clause_features;
+    a.reward = reward; a.reward_cols = reward_cols; a.done = done; a.done_cols = done_cols; a.solved = solved;
+    a.num_unsat = num_unsatisfied; a.episode_step = episode_step; a.B = B;
+    if (B == 0) return cuda_rc(launch_rng_chain(rng_in, chain_out, (cudaStream_t)stream));
+    return cuda_rc(launch_env(plan, MODE_STEP, a, (cudaStream_t)stream));
+}
+
 int msat_get_obs(const msat_plan* plan, const void* bank, int32_t P, const uint32_t* state, int32_t* obs, int32_t B,
                  void* stream) {
     if (!plan || B < 0 || P <= 0) return MSAT_EINVAL;

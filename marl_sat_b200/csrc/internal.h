@@ -46,6 +46,8 @@ struct EnvArgs {
     uint32_t Bg, env_off;       // global batch size and this shard's first global env index
     int auto_reset;
     int32_t* obs;
+    int32_t* gnn_assign;        // optional GNN-input outputs of the state the caller continues from
+    float* gnn_cf;              // (learner:165-195): assignment int32[B,n], clause_features float[B,m,3]
     float* reward;
     int reward_cols;
     uint8_t* done;

@@ -265,6 +265,25 @@ __device__ __forceinline__ void emit_obs(const Dims& d, int e, const uint32_t* a
     }
 }
 
+// Dynamic GNN input of the env's (post-reset) state straight from the shared-memory formula record
+// (learner:165-195): assignment int32[n]; clause_features float[m][3] = {is_sat, #true literals / 3.0, 1}.
+// Lets a GNN-style consumer skip the local observations altogether.
+template <int GS>
+__device__ __forceinline__ void emit_gnn(const Dims& d, int e, const uint16_t* lits, const uint32_t* assign,
+                                         int32_t* __restrict__ gnn_assign, float* __restrict__ gnn_cf, int gt) {
+    if (gnn_assign)
+        for (int v = gt; v < d.n; v += GS) gnn_assign[(size_t)e * d.n + v] = (int)((assign[v >> 5] >> (v & 31)) & 1u);
+    if (gnn_cf)
+        for (int c = gt; c < d.m; c += GS) {
+            int ntrue = 0;
+            for (int j = 0; j < d.k; ++j) ntrue += literal_true(lits[lit_index(d.m, c, j)], assign) ? 1 : 0;
+            float* o = gnn_cf + ((size_t)e * d.m + c) * 3;
+            o[0] = ntrue > 0 ? 1.0f : 0.0f;
+            o[1] = __fdiv_rn((float)ntrue, 3.0f);       // the literal 3.0 of learner:185 for every clause width
+            o[2] = 1.0f;
+        }
+}
+
 // =====================================================================================
 // K_env<GS, MODE>: reset / step (+ fused auto-reset) / get_obs.  256-thread CTAs, 256/GS envs each.
 // =====================================================================================
@@ -409,6 +428,7 @@ __global__ void __launch_bounds__(kCtaThreads) env_kernel(const Dims d, const En
         uint32_t* sout = a.state_out + (size_t)e * d.state_words;
         for (int i = gt; i < d.state_words; i += GS) sout[i] = st[i];
     }
+    if (a.gnn_assign || a.gnn_cf) emit_gnn<GS>(d, e, lits, st, a.gnn_assign, a.gnn_cf, gt);
     if (a.obs) emit_obs<GS>(d, e, st, satw, X, smx, mflat, a.obs, gid, gt);
 }
 

@@ -114,7 +114,7 @@ class VecSATEnv:
 
     def __init__(self, env: SATEnv, problems: FormulaBank | torch.Tensor, num_envs: int, key,
                  world_size: int = 1, rank: int = 0, emit_obs: bool = True, fused_keys: bool = True,
-                 compact_outputs: bool = False):
+                 compact_outputs: bool = False, gnn_outputs: bool = False):
         self.env = env
         self.fused_keys = fused_keys
         dev = env._require_cuda()
@@ -129,6 +129,11 @@ class VecSATEnv:
         self.reset_keys = torch.empty((B, 2), dtype=torch.int32, device=dev)
         self.out = env.alloc_step_outputs(B, d, want_obs=emit_obs, compact=compact_outputs)
         self._split_tmp = torch.empty(4, dtype=torch.int32, device=dev)
+        # GNN-style consumers: the step emits assignment / clause features instead of local observations
+        self.gnn_outputs = gnn_outputs
+        if gnn_outputs:
+            self.out["gnn_assignment"] = torch.empty((B, d.n), dtype=torch.int32, device=dev)
+            self.out["gnn_clause_features"] = torch.empty((B, d.m, 3), dtype=torch.float32, device=dev)
 
     # runner:289-295 -- key,_rng = split(key); idx = randint(_rng,...); reset_keys = split(_rng, B)
     def reset(self) -> Optional[torch.Tensor]:
@@ -146,6 +151,8 @@ class VecSATEnv:
         """One rollout step (learner:397-464) for this shard.  ``actions`` int32 ``[B, A]`` (mode 0) or
         ``[B, A, V]`` (mode 1) on the device.  Returns the output dict (obs of the state to continue
         from; reward/done/info are the pre-reset values, learner:467-478)."""
+        if self.gnn_outputs:
+            return self._step_gnn(actions)
         if out is None and self.fused_keys:
             return self._step_fast(actions)
         out = self.out if out is None else out
@@ -167,6 +174,20 @@ class VecSATEnv:
                         self.bank.num_problems, self.new_problem_idx, self.reset_keys)
         self.env.step_into(self.bank, self.state, self.state, actions, out, auto_reset=True,
                            new_problem_idx=self.new_problem_idx, reset_keys=self.reset_keys)
+        return out
+
+    def _step_gnn(self, actions: torch.Tensor) -> Dict[str, torch.Tensor]:
+        """Rollout step that emits the dynamic GNN input instead of local observations
+        (``msat_rollout_step_gnn``); combine with ``features.static_graph(bank)`` for the full ``GNNInput``."""
+        out = self.out
+        done, reward = out["done"], out["reward"]
+        _lib.check(self.env._lib.msat_rollout_step_gnn(
+            self.bank.plan.handle, _ptr(self.bank.data), self.bank.num_problems, _ptr(self.state), _ptr(self.state),
+            _ptr(actions), _ptr(self.keys.chain), _ptr(self.keys.next_chain), self.num_envs_global, self.env_offset,
+            _ptr(out["gnn_assignment"]), _ptr(out["gnn_clause_features"]), _ptr(reward), int(reward.shape[-1]),
+            _ptr(done), int(done.shape[-1]), _ptr(out["solved"]), _ptr(out["num_unsatisfied"]),
+            _ptr(out["episode_step"]), self.num_envs, _stream_ptr(self.state.device)), "msat_rollout_step_gnn")
+        self.keys.flip()
         return out
 
     def _step_fast(self, actions: torch.Tensor) -> Dict[str, torch.Tensor]:

@@ -104,3 +104,31 @@ def test_flip_gains_and_greedy_labels_match_brute_force(n, m, k, vpa, kind, tau)
         exp_labels, exp_delta = ofeat.greedy_labels(ref, cl[b], assign[b], tau)
         assert np.array_equal(to_np(delta[b]), exp_delta), b
         assert np.array_equal(to_np(labels[b]), exp_labels), b
+
+
+def test_fused_gnn_rollout_step_matches_separate_kernels_and_oracle():
+    """msat_rollout_step_gnn: the step emits the dynamic GNN input of the state it continues from (post
+    auto-reset) instead of local observations; identical to msat_gnn_dynamic on that state and to the oracle."""
+    from oracle import rollout as orollout
+    from oracle import threefry as otf
+    M, cl, keys, ref, env = _setup(35, 149, 3, 7, "uniform", B=9, max_steps=2)
+    B, P = 45, 9
+    key0 = otf.prng_key(3)
+    vec = M.VecSATEnv(env, cl, B, key0, emit_obs=False, compact_outputs=True, gnn_outputs=True)
+    vec.reset()
+    key, idx0, rk0 = orollout.initial_reset_inputs(key0, B, P)
+    _, st_r = ref.reset(cl[idx0], rk0)
+    rng = np.random.default_rng(1)
+    for t in range(5):
+        acts = rng.integers(0, ref.max_vars_per_agent + 1, size=(B, ref.num_agents)).astype(np.int32)
+        ks = orollout.rollout_keys(key, B, P)
+        key = ks["rng"]
+        _, st_r, rew_r, done_r, _ = orollout.env_step_with_autoreset(ref, st_r, acts, cl, ks["new_problem_indices"],
+                                                                      ks["reset_keys"])
+        out = vec.step(torch.from_numpy(acts).cuda())
+        exp = ofeat.state_to_gnn_input(ref, st_r)
+        assert np.array_equal(to_np(out["gnn_assignment"]), exp["assignment"]), t
+        assert np.array_equal(to_np(out["gnn_clause_features"]), exp["clause_features"]), t
+        assign2, cf2 = M.dynamic_features(vec.sat_state())
+        assert torch.equal(assign2, out["gnn_assignment"]) and torch.equal(cf2, out["gnn_clause_features"])
+        assert np.array_equal(to_np(out["done"][:, -1]).astype(bool), done_r)
