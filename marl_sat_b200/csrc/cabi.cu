@@ -94,6 +94,12 @@ int msat_plan_create(msat_plan** out, int32_t n, int32_t m, int32_t k, int32_t A
     p->group_threads = gs;
     p->group_smem_bytes = L.total;
     p->smem_bytes = L.total * (kCtaThreads / gs);
+    // launches that write no observations (emit_obs off, GNN-input mode) have ~m clause evaluations of work per
+    // env: one warp per env unless the caller pinned the group size or eight groups do not fit in shared memory
+    int gn = group_threads ? gs : 32;
+    while (gn < gs && (long long)L.total * (kCtaThreads / gn) > kMaxSmem) gn *= 2;
+    p->group_threads_noobs = gn;
+    p->smem_bytes_noobs = L.total * (kCtaThreads / gn);
     p->compile_smem_bytes = 4 * (m + n) * d.agw;
     if (p->compile_smem_bytes > kMaxSmem) { delete p; return MSAT_EUNSUPPORTED; }
     *out = p;

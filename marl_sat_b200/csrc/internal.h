@@ -7,6 +7,8 @@ struct msat_plan {
     int group_threads;     // GS: threads cooperating on one env (32/64/128/256)
     int group_smem_bytes;  // shared memory per env group (multiple of 128)
     int smem_bytes;        // dynamic shared memory per 256-thread CTA
+    int group_threads_noobs;   // GS used when a launch writes no observations (little per-env work: small groups)
+    int smem_bytes_noobs;
     int compile_smem_bytes;
 };
 

@@ -433,7 +433,7 @@ __global__ void __launch_bounds__(kCtaThreads) env_kernel(const Dims d, const En
 }
 
 template <int GS>
-static cudaError_t launch_env_gs(const msat_plan* plan, EnvMode mode, const EnvArgs& a, cudaStream_t s) {
+static cudaError_t launch_env_gs(const msat_plan* plan, EnvMode mode, const EnvArgs& a, cudaStream_t s, int smem_bytes) {
     const int groups = kCtaThreads / GS;
     const int grid = (a.B + groups - 1) / groups;
     if (grid == 0) return cudaSuccess;
@@ -443,22 +443,27 @@ static cudaError_t launch_env_gs(const msat_plan* plan, EnvMode mode, const EnvA
         case MODE_STEP: fn = (const void*)env_kernel<GS, MODE_STEP>; break;
         default: fn = (const void*)env_kernel<GS, MODE_OBS>; break;
     }
-    if (plan->smem_bytes > 48 * 1024) {
-        cudaError_t err = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, plan->smem_bytes);
+    if (smem_bytes > 48 * 1024) {
+        cudaError_t err = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
         if (err != cudaSuccess) return err;
     }
     Dims d = plan->d;
     EnvArgs args = a;
     void* params[] = {&d, &args};
-    return cudaLaunchKernel(fn, dim3(grid), dim3(kCtaThreads), params, (size_t)plan->smem_bytes, s);
+    return cudaLaunchKernel(fn, dim3(grid), dim3(kCtaThreads), params, (size_t)smem_bytes, s);
 }
 
 cudaError_t launch_env(const msat_plan* plan, EnvMode mode, const EnvArgs& a, cudaStream_t s) {
-    switch (plan->group_threads) {
-        case 32: return launch_env_gs<32>(plan, mode, a, s);
-        case 64: return launch_env_gs<64>(plan, mode, a, s);
-        case 128: return launch_env_gs<128>(plan, mode, a, s);
-        default: return launch_env_gs<256>(plan, mode, a, s);
+    // the group size follows the work per env: observation-writing launches use the plan's GS, launches
+    // without observations the small-group variant
+    const bool noobs = a.obs == nullptr;
+    const int gs = noobs ? plan->group_threads_noobs : plan->group_threads;
+    const int smem = noobs ? plan->smem_bytes_noobs : plan->smem_bytes;
+    switch (gs) {
+        case 32: return launch_env_gs<32>(plan, mode, a, s, smem);
+        case 64: return launch_env_gs<64>(plan, mode, a, s, smem);
+        case 128: return launch_env_gs<128>(plan, mode, a, s, smem);
+        default: return launch_env_gs<256>(plan, mode, a, s, smem);
     }
 }
 
