@@ -7,7 +7,7 @@ Follows ``/root/reference/src/learners/mappo_gnn_sat_learner.py:383-480`` (one
 from __future__ import annotations
 
 from dataclasses import fields, replace
-from typing import Dict, Tuple
+from typing import Dict
 
 import numpy as np
 
