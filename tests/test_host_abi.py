@@ -119,3 +119,52 @@ def test_config_reader_mirrors_runner_mapping(tmp_path):
     assert flat["NUM_VARS"] == 35 and flat["NUM_ENVS"] == 128
     env = config.make_env(cfg, verbose=False, device="cpu")
     assert env.num_agents == 5 and env.max_steps == 512 and env.r_sat == 20.0 and env.gamma == 0.995
+
+
+def test_rollout_step_argument_validation():
+    """The fused rollout step rejects overlapping rng buffers, shards outside the global batch and bad
+    column counts before anything is enqueued (header contract)."""
+    lib = _lib.load()
+    env = M.SATEnv(20, 91, 8, verbose=False, device="cpu")
+    plan = env._plan_for(3).handle
+    buf = (C.c_uint32 * 64)()
+    base = C.addressof(buf)
+    a128 = (base + 127) & ~127                       # a 128-byte aligned fake "device" address inside buf
+    rng, chain = a128, a128 + 4                      # overlapping: chain_out starts inside rng_in
+    call = lambda rng_in, chain_out, Bg, off, B, rcols=1, dcols=1: lib.msat_rollout_step(
+        plan, a128, 1, a128, a128, a128, rng_in, chain_out, Bg, off, None, a128, rcols, a128, dcols, None, None, None,
+        B, None)
+    assert call(rng, chain, 16, 0, 4) == _lib.MSAT_EINVAL
+    assert call(a128, a128 + 64, 16, 14, 4) == _lib.MSAT_EINVAL          # shard [14, 18) exceeds the batch of 16
+    assert call(a128, a128 + 64, 16, 0, 4, rcols=0) == _lib.MSAT_EINVAL
+    assert call(a128, a128 + 64, 16, 0, 4, dcols=0) == _lib.MSAT_EINVAL
+    assert call(None, a128 + 64, 16, 0, 4) == _lib.MSAT_EINVAL
+    assert lib.msat_rollout_step_gnn(plan, a128, 1, a128, a128, a128, rng, chain, 16, 0, None, None, None, 0, None, 0,
+                                     None, None, None, 4, None) == _lib.MSAT_EINVAL
+    assert lib.msat_flip_gains(plan, None, 1, None, 4, 0.0, None, None, None) == _lib.MSAT_EINVAL
+    assert lib.msat_gnn_dynamic(plan, None, 1, None, 4, None, None, None) == _lib.MSAT_EINVAL
+    assert lib.msat_rollout_metrics(None, 1, 1, None, None, None, None, 2, 2, None, None) == _lib.MSAT_EINVAL
+
+
+def test_dimacs_native_argument_validation():
+    lib = _lib.load()
+    rows, width = C.c_int32(), C.c_int32()
+    assert lib.msat_dimacs_parse(None, 0, 0, None, None, C.byref(rows), C.byref(width), None, 0) == _lib.MSAT_EINVAL
+    text = b"p cnf 3 1\n1 -2 3 0\n"
+    assert lib.msat_dimacs_parse(text, len(text), 0, None, None, C.byref(rows), C.byref(width), None, 0) == 0
+    assert (rows.value, width.value) == (1, 3)
+    out = (C.c_int32 * 2)()
+    assert lib.msat_dimacs_parse(text, len(text), 0, None, None, C.byref(rows), C.byref(width), out, 2) == _lib.MSAT_EINVAL
+    bad = b"p cnf\n1 2 0\n"
+    assert lib.msat_dimacs_parse(bad, len(bad), 0, None, None, C.byref(rows), C.byref(width), None, 0) == _lib.MSAT_EINVAL
+
+
+def test_plan_groups_for_baseline_shapes():
+    """Group sizes chosen by msat_plan_create for the BASELINE shapes (profiles/r1_group_size_sweep.md)."""
+    expect = {(20, 91, None): 32, (50, 218, None): 32, (100, 430, None): 256, (250, 1065, None): 256,
+              (100, 430, 7): 128, (35, 149, 7): 32}
+    for (n, m, vpa), gs in expect.items():
+        env = M.SATEnv(n, m, 512, vars_per_agent=vpa, verbose=False, device="cpu")
+        assert env._plan_for(3).dims.group_threads == gs, (n, m, vpa)
+    forced = M.SATEnv(100, 430, 512, verbose=False, device="cpu", group_threads=64)
+    assert forced._plan_for(3).dims.group_threads == 64
