@@ -307,6 +307,43 @@ class RolloutBuffer:
         """``Transition.global_done`` = done["__all__"] (learner:468), dense uint8 ``[T, B]``."""
         return self.done[:, :, 0]
 
+    @property
+    def reward_per_agent(self) -> torch.Tensor:
+        """``Transition.reward`` ``[T, B, A]`` (learner:471) as a broadcast view of the team reward: every
+        agent's reward is the same scalar (env:193-196)."""
+        return self.reward.expand(self.num_steps, self.num_envs, self.env.num_agents)
+
+    @property
+    def info(self) -> Dict[str, torch.Tensor]:
+        """``Transition.info`` (learner:475; env:278-282), ``[T, B]`` each."""
+        return {"solved": self.solved.view(torch.bool), "num_unsatisfied": self.num_unsatisfied,
+                "episode_step": self.episode_step}
+
+    def pre_step_state(self, t: int) -> SATState:
+        """The state the policy acted on at step t (source of ``Transition.local_obs`` / ``global_state`` /
+        ``agent_*_masks``, learner:386-387,473-474)."""
+        return SATState(self.env, self.bank, self.state[t], True)
+
     def local_obs(self, t: int) -> torch.Tensor:
         """Observations the policy saw at step t (``Transition.local_obs``, learner:473)."""
-        return self.env.get_obs_array(SATState(self.env, self.bank, self.state[t], True))
+        return self.env.get_obs_array(self.pre_step_state(t))
+
+    def collect(self, vec: "VecSATEnv", policy_fn) -> None:
+        """``lax.scan(_env_step, carry, None, NUM_STEPS)`` (learner:383-495) for this shard: for each step the
+        pre-step state is recorded, ``policy_fn(t, vec) -> (actions, value | None, log_prob | None)`` is
+        asked for the joint action (device tensors; it may read ``vec.out['obs']`` / ``vec.state`` and the
+        sampling key ``vec.keys`` will hold after this step is ``act_key``), and the fused step writes
+        reward / done / info of step t straight into row t of this buffer (pre-reset values, learner:467-478).
+        Everything is enqueue-only on the current stream."""
+        if vec.num_envs != self.num_envs:
+            raise ValueError(f"buffer holds {self.num_envs} envs, the vectorised env {vec.num_envs}")
+        obs = vec.out.get("obs")
+        for t in range(self.num_steps):
+            self.state[t].copy_(vec.state)
+            actions, value, log_prob = policy_fn(t, vec)
+            self.action[t].copy_(actions.reshape(self.action[t].shape))
+            if value is not None:
+                self.value[t].copy_(value)
+            if log_prob is not None:
+                self.log_prob[t].copy_(log_prob.reshape(self.log_prob[t].shape))
+            vec.step(self.action[t], out=self.step_outputs(t, obs))

@@ -74,3 +74,49 @@ def env_step_with_autoreset(env: SATEnvOracle, state: SATState, actions: np.ndar
     final_obs = _select(done_all, obs_ra, obs_a)
     reward = np.stack([rewards[a] for a in env.agents], axis=-1)               # learner:471
     return final_obs, final_state, reward, done_all, infos
+
+
+def rollout_T(env: SATEnvOracle, problems_clauses: np.ndarray, key0: np.ndarray, actions: np.ndarray,
+              values: np.ndarray | None = None):
+    """T rollout steps structured like the reference's ``lax.scan(_env_step, ...)`` (learner:383-495),
+    starting from the runner's initial reset (runner:289-295), with the policy replaced by the given
+    action table ``actions[T,B,A(,V)]`` (and ``values[T,B]``).  Returns ``(transition, final)``:
+
+    ``transition`` -- the stacked ``Transition`` fields (learner:467-478): ``local_obs[T,B,A,D]`` and the
+    GNN-input leaves are those of the state the policy acted on (**pre-step**); ``reward[T,B,A]``,
+    ``global_done[T,B]`` and ``info`` are the **pre-reset** results of that step; ``agent_clause_masks`` /
+    ``agent_neighbor_masks`` belong to the pre-step state.
+    ``final`` -- the carry after the last step: state, obs, rng, plus the per-step ``act_key`` chain.
+    """
+    from .features import state_to_gnn_input
+    T, B = actions.shape[0], actions.shape[1]
+    P = problems_clauses.shape[0]
+    rng, idx0, keys0 = initial_reset_inputs(np.asarray(key0, np.uint32), B, P)
+    obs, state = env.reset(problems_clauses[idx0], keys0)
+    obs = np.stack([obs[a] for a in env.agents], axis=1)
+    tr = {k: [] for k in ("global_done", "action", "value", "reward", "local_obs", "gs_assignment",
+                          "gs_clause_features", "info_solved", "info_num_unsatisfied", "info_episode_step",
+                          "agent_clause_masks", "agent_neighbor_masks", "act_key")}
+    initial = {"obs": obs, "state": state, "problem_idx": idx0, "reset_keys": keys0, "rng": rng}
+    for t in range(T):
+        gs = state_to_gnn_input(env, state)
+        tr["local_obs"].append(obs)                                           # learner:473 (last_local_obs)
+        tr["gs_assignment"].append(gs["assignment"])                          # learner:474 (last_global_state)
+        tr["gs_clause_features"].append(gs["clause_features"])
+        tr["agent_clause_masks"].append(state.agent_clause_masks)             # learner:386-387
+        tr["agent_neighbor_masks"].append(state.agent_neighbor_masks)
+        ks = rollout_keys(rng, B, P)
+        rng = ks["rng"]
+        tr["act_key"].append(ks["act_key"])
+        obs, state, reward, done_all, infos = env_step_with_autoreset(
+            env, state, actions[t], problems_clauses, ks["new_problem_indices"], ks["reset_keys"])
+        tr["global_done"].append(done_all)                                    # learner:468
+        tr["action"].append(actions[t])
+        tr["value"].append(values[t] if values is not None else np.zeros((B,), np.float32))
+        tr["reward"].append(reward)                                           # learner:471
+        tr["info_solved"].append(infos["solved"])
+        tr["info_num_unsatisfied"].append(infos["num_unsatisfied"])
+        tr["info_episode_step"].append(infos["episode_step"])
+    transition = {k: np.stack(v) for k, v in tr.items()}
+    final = {"obs": obs, "state": state, "rng": rng, "initial": initial}
+    return transition, final
