@@ -3,7 +3,7 @@
 ``create_static_graph``: /root/reference/src/utils/graph_constructor.py:93-114;
 ``state_to_gnn_input``: /root/reference/src/learners/mappo_gnn_sat_learner.py:149-195;
 ``rollout_metrics``: learner:661-686; ``evaluate_policy``: /root/reference/src/runners/mappo_runner.py:30-73.
-**Parity unpinned** (no reference fixtures for these; see oracle/__init__.py).
+Pinned by reference-generated fixtures (``tests/test_golden_env.py``; see oracle/__init__.py).
 """
 from __future__ import annotations
 

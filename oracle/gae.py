@@ -2,8 +2,9 @@
 (test oracle / CPU baseline only).
 
 Follows ``/root/reference/src/learners/mappo_gnn_sat_learner.py:504-532``.
-**Parity unpinned** (no reference fixture); tolerance on the CUDA path is 1e-5
-relative as stated by BASELINE.json's north_star.
+Pinned: bit-identical to the reference's own ``_calculate_gae`` run under the NumPy stand-ins
+(``tests/test_golden_env.py``); tolerance on the CUDA path is 1e-5 relative as stated by
+BASELINE.json's north_star.
 """
 from __future__ import annotations
 

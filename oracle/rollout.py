@@ -2,7 +2,7 @@
 
 Follows ``/root/reference/src/learners/mappo_gnn_sat_learner.py:383-480`` (one
 ``_env_step`` minus the policy) and ``/root/reference/src/runners/mappo_runner.py:289-295``
-(initial reset).  **Parity unpinned** (see ``oracle/__init__.py``).
+(initial reset).  Pinned by reference-generated fixtures (``tests/test_golden_env.py``; see ``oracle/__init__.py``).
 """
 from __future__ import annotations
 

@@ -2,9 +2,9 @@
 
 Follows ``/root/reference/src/envs/multi_agent_sat_env.py`` function by
 function; every array carries a leading batch axis ``B`` where the reference
-relies on ``jax.vmap`` (runner:137, learner:418).  **Parity unpinned**: the
-reference has no golden vectors for this path and cannot be executed here (no
-JAX); see ``oracle/__init__.py`` for what anchors this restatement.
+relies on ``jax.vmap`` (runner:137, learner:418).  Pinned: it reproduces, bit for
+bit, the fixtures ``tests/golden/env_*.npz`` that the reference's own unmodified
+source produced (``tests/golden/make_golden_env.py``; see ``oracle/__init__.py``).
 
 JAX indexing semantics that matter and are reproduced here:
 * negative gather indices wrap once (``x[-1]`` is the last element), indices

@@ -8,7 +8,7 @@
  * reference's own structure: every env is stepped, every env is reset on its newly drawn
  * formula, and every state/observation leaf is then selected by done (no incremental
  * shortcuts), so that it can serve as the compiled multi-threaded CPU baseline of bench.py.
- * Parity unpinned for the env semantics (see oracle/__init__.py); the PRNG follows
+ * Pinned by the reference-generated fixtures tests/golden/env_*.npz (tests/test_golden_env.py); the PRNG follows
  * oracle/threefry.py (pinned by known-answer vectors).
  *
  * Build: gcc -O2 -fopenmp -shared -fPIC -o oracle/_build/liboracle_c.so oracle/sat_env_c.c

@@ -173,6 +173,35 @@ def test_oracle_eval_and_bc_labels_match_reference(name):
             eq(lab, fx["bc_labels"][ti, p], f"bc labels tau={tau} p={p}")
 
 
+@pytest.mark.parametrize("name", ROLLOUT_CASES)
+def test_c_port_rollout_matches_reference(name):
+    """The plain-C/OpenMP restatement (the compiled CPU baseline of bench.py) against the same fixtures."""
+    from oracle.c_port import SATEnvOracleC
+    fx = load(name)
+    c = fx["cfg"]
+    cen = SATEnvOracleC(c["n"], c["m"], c["max_steps"], vars_per_agent=c["vpa"], action_mode=c["mode"])
+    st = cen.reset(fx["clauses"][fx["initial_indices"]], fx["initial_reset_keys"])
+    eq(st["obs"], fx["obs0"], "obs0")
+    rng = fx["rng_after_init"]
+    for t in range(c["T"]):
+        eq(st["obs"], fx["tr_local_obs"][t], f"local_obs[{t}]")
+        chain, idx, keys = cen.rollout_keys(rng, c["B"], c["P"])
+        rng = chain[0:2].copy()
+        eq(chain[2:4], fx["act_keys"][t], f"act_key[{t}]")
+        out = cen.step(st, fx["actions"][t], fx["clauses"], idx, keys)
+        eq(out["reward"], fx["tr_reward"][t], f"reward[{t}]")
+        eq(out["done_all"], fx["tr_global_done"][t], f"done[{t}]")
+        eq(out["solved"], fx["tr_info_solved"][t], f"solved[{t}]")
+        eq(out["num_unsatisfied"], fx["tr_info_num_unsatisfied"][t], f"num_unsatisfied[{t}]")
+        eq(out["episode_step"], fx["tr_info_episode_step"][t], f"episode_step[{t}]")
+    eq(st["obs"], fx["final_obs"], "final obs")
+    eq(rng, fx["final_rng"], "final rng")
+    for c_name, leaf in [("assign", "variable_assignments"), ("status", "clauses_satisfied_status"),
+                         ("nunsat", "num_unsatisfied"), ("step", "step"), ("done", "done"), ("clauses", "clauses"),
+                         ("acm", "agent_clause_masks"), ("anm", "agent_neighbor_masks"), ("l2a", "literal_to_agent_idx")]:
+        eq(st[c_name], fx[f"final_{leaf}"], f"final.{leaf}")
+
+
 # ---------------------------------------------------------------------------------------------------------
 # CUDA path == reference fixtures (GPU, through the C ABI)
 # ---------------------------------------------------------------------------------------------------------
