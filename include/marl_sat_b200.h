@@ -71,6 +71,16 @@ int msat_plan_create(msat_plan** out, int32_t num_vars, int32_t num_clauses, int
                      int32_t num_agents, int32_t action_mode, int32_t max_steps, int32_t group_threads);
 void msat_plan_destroy(msat_plan* plan);
 int msat_plan_dims(const msat_plan* plan, msat_dims* out);
+
+/* Reward variant of every step entry point that uses this plan (call before the first launch):
+ *   MSAT_REWARD_SPARSE (default)  the active reward of the reference, 1.0 when solved else 0.0 (env:183-198);
+ *   MSAT_REWARD_SHAPED            the reference's alternative team reward (commented out at env:201-223):
+ *        gamma * (-unsat') - (-unsat) + r_clause * #newly satisfied clauses + [solved] * r_sat
+ *     in float32 with the reference's operation order; gamma / r_clause / r_sat are the constructor
+ *     arguments the reference stores for it (env:40-42). */
+#define MSAT_REWARD_SPARSE 0
+#define MSAT_REWARD_SHAPED 1
+int msat_plan_set_reward(msat_plan* plan, int32_t mode, double gamma, double r_clause, double r_sat);
 /* Reference grouping rule (env:294-338): number of agents for (n, vars_per_agent);
  * vars_per_agent <= 0 means "auto" (n/4 if 4 | n else max(2, floor(sqrt(n)))). */
 int32_t msat_num_agents_for(int32_t num_vars, int32_t vars_per_agent);
@@ -112,13 +122,15 @@ int msat_reset(const msat_plan* plan, const void* bank, int32_t num_problems,
  *                  (A+1 = one per agent plus "__all__", env:260-261; 1 = Transition.global_done
  *                  only, learner:468); pre-reset values
  *   solved uint8[B], num_unsatisfied int32[B], episode_step int32[B]  (infos, env:278-282)
- * Any of reward/done/solved/num_unsatisfied/episode_step may be NULL. */
+ *   newly_satisfied int32[B]: clauses satisfied after the step that were not before it (env:211);
+ *                  only with MSAT_REWARD_SHAPED (else must be NULL)
+ * Any of reward/done/solved/num_unsatisfied/episode_step/newly_satisfied may be NULL. */
 int msat_step(const msat_plan* plan, const void* bank, int32_t num_problems,
               const uint32_t* state_in, uint32_t* state_out, const int32_t* actions,
               int32_t auto_reset, const int32_t* new_problem_idx, const uint32_t* reset_keys,
               int32_t* obs, float* reward, int32_t reward_cols, uint8_t* done, int32_t done_cols,
               uint8_t* solved, int32_t* num_unsatisfied, int32_t* episode_step,
-              int32_t num_envs, void* stream);
+              int32_t* newly_satisfied, int32_t num_envs, void* stream);
 
 /* One whole rollout step of the learner's `_env_step` env half (learner:397-464) in ONE launch:
  * msat_rng_chain + msat_env_keys + msat_step(auto_reset=1) fused.  The kernel advances the rollout
@@ -148,6 +160,26 @@ int msat_rollout_step_gnn(const msat_plan* plan, const void* bank, int32_t num_p
                           float* reward, int32_t reward_cols, uint8_t* done, int32_t done_cols,
                           uint8_t* solved, int32_t* num_unsatisfied, int32_t* episode_step,
                           int32_t num_envs, void* stream);
+
+/* K rollout steps in ONE launch (1 <= K <= 64) for callers whose actions do not depend on the intermediate
+ * observations -- replaying an action table, open-loop evaluation (runner:30-73 with a fixed plan), or
+ * small batches where one launch per step is launch-bound.  Each env group keeps its state and formula in
+ * shared memory across the K steps and re-stages the formula only after an auto-reset.
+ *   actions          int32 [K, B, A] (mode 0) or [K, B, A, V] (mode 1)
+ *   chain_out        the chain of the LAST step; rng_in -> K applications of learner:397-434
+ *   obs / gnn_*      with emit_every_step != 0: [K, B, ...] (the policy input after every step), else
+ *                    [B, ...] of the final state only; at most one of obs / gnn_* kinds per launch
+ *   reward, done, solved, num_unsatisfied, episode_step, newly_satisfied: [K, B, ...] (row j = step j,
+ *                    pre-reset values, learner:467-478); any may be NULL
+ * Results are identical to K calls of msat_rollout_step / msat_rollout_step_gnn. */
+int msat_rollout_steps(const msat_plan* plan, const void* bank, int32_t num_problems,
+                       const uint32_t* state_in, uint32_t* state_out, const int32_t* actions, int32_t num_steps,
+                       const uint32_t* rng_in, uint32_t* chain_out,
+                       int32_t num_envs_global, int32_t env_offset,
+                       int32_t* obs, int32_t* gnn_assignment, float* gnn_clause_features, int32_t emit_every_step,
+                       float* reward, int32_t reward_cols, uint8_t* done, int32_t done_cols,
+                       uint8_t* solved, int32_t* num_unsatisfied, int32_t* episode_step, int32_t* newly_satisfied,
+                       int32_t num_envs, void* stream);
 
 /* Replaces `SATEnv.get_obs(state)` (env:345-398): obs int32[B,A,D] from a state. */
 int msat_get_obs(const msat_plan* plan, const void* bank, int32_t num_problems,
@@ -184,6 +216,36 @@ int msat_rollout_step_host(const msat_plan* plan, const void* bank, int32_t num_
                            float* reward_host, uint8_t* done_host, uint8_t* solved_host,
                            int32_t* num_unsatisfied_host, int32_t* episode_step_host,
                            int32_t num_envs, void* stream);
+
+/* Asynchronous, double-buffered variant of msat_rollout_step_host.  A pipe owns two copy streams and
+ * `depth` (1..4) slots of events on the device that is current at creation.  msat_rollout_step_host_async
+ * enqueues -- without blocking the host -- the upload of `actions_host` (pinned) on the copy-in stream,
+ * the fused step on `stream`, and the download of the results into the `*_host` buffers (pinned) on the
+ * copy-out stream, ordered by events; msat_host_wait(pipe, slot) blocks until that slot's results are in
+ * host memory.  Calls with different slots must use different actions_dev / result buffers (device and
+ * host); with depth 2 the upload of step t+1 and the download of step t-1 overlap the kernel of step t.
+ * Steps execute in call order (the state is updated in place on `stream`). */
+typedef struct msat_host_pipe msat_host_pipe;
+int msat_host_pipe_create(msat_host_pipe** out, int32_t depth);
+void msat_host_pipe_destroy(msat_host_pipe* pipe);
+int msat_rollout_step_host_async(msat_host_pipe* pipe, int32_t slot,
+                                 const msat_plan* plan, const void* bank, int32_t num_problems,
+                                 uint32_t* state, const int32_t* actions_host, int32_t* actions_dev,
+                                 const uint32_t* rng_in, uint32_t* chain_out,
+                                 int32_t num_envs_global, int32_t env_offset,
+                                 int32_t* obs_dev, float* reward_dev, int32_t reward_cols,
+                                 uint8_t* done_dev, int32_t done_cols, uint8_t* solved_dev,
+                                 int32_t* num_unsatisfied_dev, int32_t* episode_step_dev,
+                                 float* reward_host, uint8_t* done_host, uint8_t* solved_host,
+                                 int32_t* num_unsatisfied_host, int32_t* episode_step_host,
+                                 int32_t num_envs, void* stream);
+int msat_host_wait(msat_host_pipe* pipe, int32_t slot);
+/* Releases the library's internal per-device streams / events (msat_rollout_step_host). */
+int msat_shutdown(void);
+
+/* Process-wide measurement knobs (A/B comparisons in bench.py; not part of the drop-in surface):
+ *   "gae_plain" 1 = msat_gae keeps the register-chunked scan instead of the cp.async-pipelined one. */
+int msat_tune(const char* key, int32_t value);
 
 /* --- rollout RNG chain (JAX 0.4.29 Threefry-2x32, non-partitionable) --------- */
 

@@ -41,7 +41,17 @@ SIGNATURES = {
     "msat_plan_dims": (C.c_int, [_p, C.POINTER(Dims)]),
     "msat_compile_bank": (C.c_int, [_p, _p, _i32, _p, _p]),
     "msat_reset": (C.c_int, [_p, _p, _i32, _p, _p, _p, _p, _i32, _p]),
-    "msat_step": (C.c_int, [_p, _p, _i32, _p, _p, _p, _i32, _p, _p, _p, _p, _i32, _p, _i32, _p, _p, _p, _i32, _p]),
+    "msat_plan_set_reward": (C.c_int, [_p, _i32, _f64, _f64, _f64]),
+    "msat_tune": (C.c_int, [C.c_char_p, _i32]),
+    "msat_step": (C.c_int, [_p, _p, _i32, _p, _p, _p, _i32, _p, _p, _p, _p, _i32, _p, _i32, _p, _p, _p, _p, _i32, _p]),
+    "msat_rollout_steps": (C.c_int, [_p, _p, _i32, _p, _p, _p, _i32, _p, _p, _i32, _i32, _p, _p, _p, _i32, _p, _i32,
+                                     _p, _i32, _p, _p, _p, _p, _i32, _p]),
+    "msat_host_pipe_create": (C.c_int, [C.POINTER(_p), _i32]),
+    "msat_host_pipe_destroy": (None, [_p]),
+    "msat_rollout_step_host_async": (C.c_int, [_p, _i32, _p, _p, _i32, _p, _p, _p, _p, _p, _i32, _i32, _p, _p, _i32, _p,
+                                               _i32, _p, _p, _p] + [_p] * 5 + [_i32, _p]),
+    "msat_host_wait": (C.c_int, [_p, _i32]),
+    "msat_shutdown": (C.c_int, []),
     "msat_rollout_step": (C.c_int, [_p, _p, _i32, _p, _p, _p, _p, _p, _i32, _i32, _p, _p, _i32, _p, _i32, _p, _p, _p, _i32, _p]),
     "msat_rollout_step_gnn": (C.c_int, [_p, _p, _i32, _p, _p, _p, _p, _p, _i32, _i32, _p, _p, _p, _i32, _p, _i32, _p, _p, _p, _i32, _p]),
     "msat_get_obs": (C.c_int, [_p, _p, _i32, _p, _p, _i32, _p]),

@@ -2,6 +2,8 @@
 // validation and kernel enqueue.  No allocation, no synchronisation (except msat_step_host, which is
 // documented to synchronise), no torch types.
 #include <math.h>
+#include <string.h>
+#include <map>
 #include <mutex>
 #include <new>
 
@@ -15,28 +17,88 @@ namespace {
 inline bool aligned(const void* p, size_t a) { return (reinterpret_cast<uintptr_t>(p) & (a - 1)) == 0; }
 inline int cuda_rc(cudaError_t e) { return e == cudaSuccess ? MSAT_OK : (int)e; }
 constexpr int kMaxSmem = 227 * 1024;
+constexpr int kMaxPipeDepth = 4;
 
-// Two internal streams + fork/join events used by msat_rollout_step_host to overlap PCIe copies with the
-// kernel; created lazily for the current device (one process drives one GPU in this design).
-struct HostPipe {
-    std::mutex mu;
-    int dev = -1;
+// Internal streams + fork/join events used by msat_rollout_step_host to overlap PCIe copies with the kernel:
+// one set per device, created on first use, released by msat_shutdown().
+struct SyncPipe {
     cudaStream_t ws[2] = {nullptr, nullptr};
     cudaEvent_t fork = nullptr, join[2] = {nullptr, nullptr};
-    cudaError_t init() {
-        int cur = 0;
-        cudaError_t e = cudaGetDevice(&cur);
-        if (e != cudaSuccess || cur == dev) return e;
+    cudaError_t create() {
+        cudaError_t e = cudaSuccess;
         for (int w = 0; w < 2 && e == cudaSuccess; ++w) {
             e = cudaStreamCreateWithFlags(&ws[w], cudaStreamNonBlocking);
             if (e == cudaSuccess) e = cudaEventCreateWithFlags(&join[w], cudaEventDisableTiming);
         }
         if (e == cudaSuccess) e = cudaEventCreateWithFlags(&fork, cudaEventDisableTiming);
-        if (e == cudaSuccess) dev = cur;
         return e;
     }
+    void destroy() {
+        for (int w = 0; w < 2; ++w) {
+            if (ws[w]) cudaStreamDestroy(ws[w]);
+            if (join[w]) cudaEventDestroy(join[w]);
+            ws[w] = nullptr; join[w] = nullptr;
+        }
+        if (fork) cudaEventDestroy(fork);
+        fork = nullptr;
+    }
 };
-HostPipe g_pipe;
+std::mutex g_pipe_mu;
+std::map<int, SyncPipe> g_pipes;      // device ordinal -> pipe
+
+// must be called with g_pipe_mu held; leaves the current device unchanged
+cudaError_t sync_pipe_for_current_device(SyncPipe** out) {
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    auto it = g_pipes.find(dev);
+    if (it == g_pipes.end()) {
+        SyncPipe sp;
+        e = sp.create();
+        if (e != cudaSuccess) { sp.destroy(); return e; }
+        it = g_pipes.emplace(dev, sp).first;
+    }
+    *out = &it->second;
+    return cudaSuccess;
+}
+
+// Device->host result copies of one batch slice; outputs that are adjacent in both address spaces (the Python
+// layer carves them out of one device block and one pinned block) travel as ONE copy.
+struct ResultBufs {
+    float* reward_dev; int32_t reward_cols; uint8_t* done_dev; int32_t done_cols; uint8_t* solved_dev;
+    int32_t* nunsat_dev; int32_t* estep_dev;
+    float* reward_host; uint8_t* done_host; uint8_t* solved_host; int32_t* nunsat_host; int32_t* estep_host;
+};
+cudaError_t copy_results(const ResultBufs& r, int b0, int bc, cudaStream_t w) {
+    struct Seg { const char* dev; char* host; size_t bytes; };
+    Seg seg[5];
+    int ns = 0;
+    auto add = [&](const void* dv, void* hs, size_t off, size_t bytes) {
+        if (dv && hs && bytes) seg[ns++] = Seg{static_cast<const char*>(dv) + off, static_cast<char*>(hs) + off, bytes};
+    };
+    add(r.reward_dev, r.reward_host, (size_t)b0 * r.reward_cols * sizeof(float), (size_t)bc * r.reward_cols * sizeof(float));
+    add(r.nunsat_dev, r.nunsat_host, (size_t)b0 * 4, (size_t)bc * 4);
+    add(r.estep_dev, r.estep_host, (size_t)b0 * 4, (size_t)bc * 4);
+    add(r.done_dev, r.done_host, (size_t)b0 * r.done_cols, (size_t)bc * r.done_cols);
+    add(r.solved_dev, r.solved_host, (size_t)b0, (size_t)bc);
+    for (int i = 1; i < ns; ++i)          // insertion sort by device address
+        for (int j = i; j > 0 && seg[j].dev < seg[j - 1].dev; --j) { Seg t = seg[j]; seg[j] = seg[j - 1]; seg[j - 1] = t; }
+    cudaError_t e = cudaSuccess;
+    for (int i = 0; i < ns && e == cudaSuccess;) {
+        Seg cur = seg[i++];
+        while (i < ns && seg[i].dev == cur.dev + cur.bytes && seg[i].host == cur.host + cur.bytes) cur.bytes += seg[i++].bytes;
+        e = cudaMemcpyAsync(cur.host, cur.dev, cur.bytes, cudaMemcpyDeviceToHost, w);
+    }
+    return e;
+}
+
+inline void fill_reward(EnvArgs& a, const msat_plan* plan, int32_t* newly) {
+    a.reward_mode = plan->reward_mode;
+    a.r_gamma = plan->r_gamma;
+    a.r_clause = plan->r_clause;
+    a.r_sat = plan->r_sat;
+    a.newly_sat = newly;
+}
 
 }  // namespace
 
@@ -58,7 +120,7 @@ int msat_plan_create(msat_plan** out, int32_t n, int32_t m, int32_t k, int32_t A
                      int32_t max_steps, int32_t group_threads) {
     if (!out) return MSAT_EINVAL;
     *out = nullptr;
-    if (n <= 0 || m <= 0 || k <= 0 || A <= 0 || A > n || n > 32767) return MSAT_EINVAL;
+    if (n <= 0 || m <= 0 || k <= 0 || A <= 0 || A > n || n > 32767 || m > 32767) return MSAT_EINVAL;
     if (action_mode != 0 && action_mode != 1) return MSAT_EINVAL;
     if ((long long)A * (2LL * n + m) > (1LL << 26)) return MSAT_EUNSUPPORTED;
     msat_plan* p = new (std::nothrow) msat_plan();
@@ -87,19 +149,22 @@ int msat_plan_create(msat_plan** out, int32_t n, int32_t m, int32_t k, int32_t A
     // spot -- larger groups idle most lanes in the short per-env phases, smaller ones serialise the stores
     if (gs == 0) gs = chunks <= 768 ? 32 : (chunks <= 1536 ? 64 : (chunks <= 3072 ? 128 : 256));
     if (gs != 32 && gs != 64 && gs != 128 && gs != 256) { delete p; return MSAT_EINVAL; }
-    const GroupLayout L = group_layout(d);
+    const GroupLayout L = group_layout(d, true);
+    const int kChain = 40 * kMaxFusedSteps;      // room for the K key chains of a multi-step launch
     // grow the group until one CTA's groups fit in shared memory
-    while (gs < 256 && (long long)L.total * (kCtaThreads / gs) > kMaxSmem) gs *= 2;
-    if ((long long)L.total * (kCtaThreads / gs) > kMaxSmem) { delete p; return MSAT_EUNSUPPORTED; }
+    while (gs < 256 && (long long)L.total * (kCtaThreads / gs) + kChain > kMaxSmem) gs *= 2;
+    if ((long long)L.total * (kCtaThreads / gs) + kChain > kMaxSmem) { delete p; return MSAT_EUNSUPPORTED; }
     p->group_threads = gs;
     p->group_smem_bytes = L.total;
     p->smem_bytes = L.total * (kCtaThreads / gs);
     // launches that write no observations (emit_obs off, GNN-input mode) have ~m clause evaluations of work per
-    // env: one warp per env unless the caller pinned the group size or eight groups do not fit in shared memory
+    // env and stage only the literal block: one warp per env unless the caller pinned the group size or eight
+    // groups do not fit in shared memory
+    const GroupLayout Ln = group_layout(d, false);
     int gn = group_threads ? gs : 32;
-    while (gn < gs && (long long)L.total * (kCtaThreads / gn) > kMaxSmem) gn *= 2;
+    while (gn < 256 && (long long)Ln.total * (kCtaThreads / gn) + kChain > kMaxSmem) gn *= 2;
     p->group_threads_noobs = gn;
-    p->smem_bytes_noobs = L.total * (kCtaThreads / gn);
+    p->smem_bytes_noobs = Ln.total * (kCtaThreads / gn);
     p->compile_smem_bytes = 4 * (m + n) * d.agw;
     if (p->compile_smem_bytes > kMaxSmem) { delete p; return MSAT_EUNSUPPORTED; }
     *out = p;
@@ -107,6 +172,21 @@ int msat_plan_create(msat_plan** out, int32_t n, int32_t m, int32_t k, int32_t A
 }
 
 void msat_plan_destroy(msat_plan* plan) { delete plan; }
+
+int msat_plan_set_reward(msat_plan* plan, int32_t mode, double gamma, double r_clause, double r_sat) {
+    if (!plan || (mode != MSAT_REWARD_SPARSE && mode != MSAT_REWARD_SHAPED)) return MSAT_EINVAL;
+    plan->reward_mode = mode;
+    plan->r_gamma = (float)gamma;
+    plan->r_clause = (float)r_clause;
+    plan->r_sat = (float)r_sat;
+    return MSAT_OK;
+}
+
+int msat_tune(const char* key, int32_t value) {
+    if (!key) return MSAT_EINVAL;
+    if (!strcmp(key, "gae_plain")) { g_gae_force_plain = value; return MSAT_OK; }
+    return MSAT_EINVAL;
+}
 
 int msat_plan_dims(const msat_plan* plan, msat_dims* o) {
     if (!plan || !o) return MSAT_EINVAL;
@@ -138,10 +218,11 @@ int msat_reset(const msat_plan* plan, const void* bank, int32_t P, const int32_t
 int msat_step(const msat_plan* plan, const void* bank, int32_t P, const uint32_t* state_in, uint32_t* state_out,
               const int32_t* actions, int32_t auto_reset, const int32_t* new_problem_idx, const uint32_t* reset_keys,
               int32_t* obs, float* reward, int32_t reward_cols, uint8_t* done, int32_t done_cols, uint8_t* solved,
-              int32_t* num_unsatisfied, int32_t* episode_step, int32_t B, void* stream) {
+              int32_t* num_unsatisfied, int32_t* episode_step, int32_t* newly_satisfied, int32_t B, void* stream) {
     if (!plan || B < 0 || P <= 0 || (done && done_cols <= 0) || (reward && reward_cols <= 0)) return MSAT_EINVAL;
     if (B > 0 && (!bank || !state_in || !state_out || !actions)) return MSAT_EINVAL;
     if (auto_reset && B > 0 && (!new_problem_idx || !reset_keys)) return MSAT_EINVAL;
+    if (newly_satisfied && plan->reward_mode != MSAT_REWARD_SHAPED) return MSAT_EINVAL;
     if (!aligned(bank, 128) || !aligned(state_in, 16) || !aligned(state_out, 16) || !aligned(obs, 16))
         return MSAT_EALIGN;
     EnvArgs a{};
@@ -151,6 +232,49 @@ int msat_step(const msat_plan* plan, const void* bank, int32_t P, const uint32_t
     a.obs = obs; a.reward = reward; a.reward_cols = reward_cols; a.done = done; a.done_cols = done_cols;
     a.solved = solved;
     a.num_unsat = num_unsatisfied; a.episode_step = episode_step; a.B = B;
+    fill_reward(a, plan, newly_satisfied);
+    return cuda_rc(launch_env(plan, MODE_STEP, a, (cudaStream_t)stream));
+}
+
+// Shared body of the fused rollout entry points: K >= 1 steps per launch, local observations or GNN inputs.
+static int rollout_launch(const msat_plan* plan, const void* bank, int32_t P, const uint32_t* state_in,
+                          uint32_t* state_out, const int32_t* actions, int32_t K, const uint32_t* rng_in,
+                          uint32_t* chain_out, int32_t Bg, int32_t env_offset, int32_t* obs, int32_t* gnn_assignment,
+                          float* gnn_clause_features, int32_t emit_every_step, float* reward, int32_t reward_cols,
+                          uint8_t* done, int32_t done_cols, uint8_t* solved, int32_t* num_unsatisfied,
+                          int32_t* episode_step, int32_t* newly_satisfied, int32_t B, void* stream) {
+    if (!plan || B < 0 || P <= 0 || (done && done_cols <= 0) || (reward && reward_cols <= 0)) return MSAT_EINVAL;
+    if (K < 1 || K > kMaxFusedSteps) return MSAT_EINVAL;
+    if (!rng_in || !chain_out || Bg <= 0 || env_offset < 0 || (long long)env_offset + B > Bg) return MSAT_EINVAL;
+    if (Bg > (1 << 30)) return MSAT_EUNSUPPORTED;
+    if (newly_satisfied && plan->reward_mode != MSAT_REWARD_SHAPED) return MSAT_EINVAL;
+    {   // the advanced chain is written while other CTAs still read rng_in: the buffers must not overlap
+        const uintptr_t r = reinterpret_cast<uintptr_t>(rng_in), c = reinterpret_cast<uintptr_t>(chain_out);
+        if (r + 8 > c && c + 40 > r) return MSAT_EINVAL;
+    }
+    if (B > 0 && (!bank || !state_in || !state_out || !actions)) return MSAT_EINVAL;
+    if (!aligned(bank, 128) || !aligned(state_in, 16) || !aligned(state_out, 16) || !aligned(obs, 16))
+        return MSAT_EALIGN;
+    const Dims& d = plan->d;
+    EnvArgs a{};
+    a.bank = static_cast<const uint8_t*>(bank); a.P = P;
+    a.state_in = state_in; a.state_out = state_out; a.actions = actions;
+    a.auto_reset = 1; a.rng_in = rng_in; a.chain_out = chain_out; a.Bg = (uint32_t)Bg; a.env_off = (uint32_t)env_offset;
+    a.obs = obs; a.gnn_assign = gnn_assignment; a.gnn_cf = gnn_clause_features;
+    a.reward = reward; a.reward_cols = reward_cols; a.done = done; a.done_cols = done_cols;
+    a.solved = solved;
+    a.num_unsat = num_unsatisfied; a.episode_step = episode_step; a.B = B;
+    a.num_steps = K;
+    a.act_step_stride = (long long)B * d.A * (d.action_mode == 0 ? 1 : d.V);
+    a.emit_every_step = emit_every_step ? 1 : 0;
+    fill_reward(a, plan, newly_satisfied);
+    if (B == 0) {
+        // an empty shard still advances the chain K times
+        cudaError_t e = cudaSuccess;
+        for (int j = 0; j < K && e == cudaSuccess; ++j)
+            e = launch_rng_chain(j == 0 ? rng_in : chain_out, chain_out, (cudaStream_t)stream);
+        return cuda_rc(e);
+    }
     return cuda_rc(launch_env(plan, MODE_STEP, a, (cudaStream_t)stream));
 }
 
@@ -159,25 +283,9 @@ int msat_rollout_step(const msat_plan* plan, const void* bank, int32_t P, const 
                       int32_t Bg, int32_t env_offset, int32_t* obs, float* reward, int32_t reward_cols, uint8_t* done,
                       int32_t done_cols, uint8_t* solved, int32_t* num_unsatisfied, int32_t* episode_step, int32_t B,
                       void* stream) {
-    if (!plan || B < 0 || P <= 0 || (done && done_cols <= 0) || (reward && reward_cols <= 0)) return MSAT_EINVAL;
-    if (!rng_in || !chain_out || Bg <= 0 || env_offset < 0 || (long long)env_offset + B > Bg) return MSAT_EINVAL;
-    if (Bg > (1 << 30)) return MSAT_EUNSUPPORTED;
-    {   // the advanced chain is written while other CTAs still read rng_in: the buffers must not overlap
-        const uintptr_t r = reinterpret_cast<uintptr_t>(rng_in), c = reinterpret_cast<uintptr_t>(chain_out);
-        if (r + 8 > c && c + 40 > r) return MSAT_EINVAL;
-    }
-    if (B > 0 && (!bank || !state_in || !state_out || !actions)) return MSAT_EINVAL;
-    if (!aligned(bank, 128) || !aligned(state_in, 16) || !aligned(state_out, 16) || !aligned(obs, 16))
-        return MSAT_EALIGN;
-    EnvArgs a{};
-    a.bank = static_cast<const uint8_t*>(bank); a.P = P;
-    a.state_in = state_in; a.state_out = state_out; a.actions = actions;
-    a.auto_reset = 1; a.rng_in = rng_in; a.chain_out = chain_out; a.Bg = (uint32_t)Bg; a.env_off = (uint32_t)env_offset;
-    a.obs = obs; a.reward = reward; a.reward_cols = reward_cols; a.done = done; a.done_cols = done_cols;
-    a.solved = solved;
-    a.num_unsat = num_unsatisfied; a.episode_step = episode_step; a.B = B;
-    if (B == 0) return cuda_rc(launch_rng_chain(rng_in, chain_out, (cudaStream_t)stream));
-    return cuda_rc(launch_env(plan, MODE_STEP, a, (cudaStream_t)stream));
+    return rollout_launch(plan, bank, P, state_in, state_out, actions, 1, rng_in, chain_out, Bg, env_offset, obs,
+                          nullptr, nullptr, 0, reward, reward_cols, done, done_cols, solved, num_unsatisfied,
+                          episode_step, nullptr, B, stream);
 }
 
 int msat_rollout_step_gnn(const msat_plan* plan, const void* bank, int32_t P, const uint32_t* state_in,
@@ -185,24 +293,21 @@ int msat_rollout_step_gnn(const msat_plan* plan, const void* bank, int32_t P, co
                           int32_t Bg, int32_t env_offset, int32_t* assignment, float* clause_features, float* reward,
                           int32_t reward_cols, uint8_t* done, int32_t done_cols, uint8_t* solved,
                           int32_t* num_unsatisfied, int32_t* episode_step, int32_t B, void* stream) {
-    if (!plan || B < 0 || P <= 0 || (done && done_cols <= 0) || (reward && reward_cols <= 0)) return MSAT_EINVAL;
-    if (!rng_in || !chain_out || Bg <= 0 || env_offset < 0 || (long long)env_offset + B > Bg) return MSAT_EINVAL;
-    if (Bg > (1 << 30)) return MSAT_EUNSUPPORTED;
-    {
-        const uintptr_t r = reinterpret_cast<uintptr_t>(rng_in), c = reinterpret_cast<uintptr_t>(chain_out);
-        if (r + 8 > c && c + 40 > r) return MSAT_EINVAL;
-    }
-    if (B > 0 && (!bank || !state_in || !state_out || !actions)) return MSAT_EINVAL;
-    if (!aligned(bank, 128) || !aligned(state_in, 16) || !aligned(state_out, 16)) return MSAT_EALIGN;
-    EnvArgs a{};
-    a.bank = static_cast<const uint8_t*>(bank); a.P = P;
-    a.state_in = state_in; a.state_out = state_out; a.actions = actions;
-    a.auto_reset = 1; a.rng_in = rng_in; a.chain_out = chain_out; a.Bg = (uint32_t)Bg; a.env_off = (uint32_t)env_offset;
-    a.gnn_assign = assignment; a.gnn_cf = clause_features;
-    a.reward = reward; a.reward_cols = reward_cols; a.done = done; a.done_cols = done_cols; a.solved = solved;
-    a.num_unsat = num_unsatisfied; a.episode_step = episode_step; a.B = B;
-    if (B == 0) return cuda_rc(launch_rng_chain(rng_in, chain_out, (cudaStream_t)stream));
-    return cuda_rc(launch_env(plan, MODE_STEP, a, (cudaStream_t)stream));
+    return rollout_launch(plan, bank, P, state_in, state_out, actions, 1, rng_in, chain_out, Bg, env_offset, nullptr,
+                          assignment, clause_features, 0, reward, reward_cols, done, done_cols, solved,
+                          num_unsatisfied, episode_step, nullptr, B, stream);
+}
+
+int msat_rollout_steps(const msat_plan* plan, const void* bank, int32_t P, const uint32_t* state_in,
+                       uint32_t* state_out, const int32_t* actions, int32_t num_steps, const uint32_t* rng_in,
+                       uint32_t* chain_out, int32_t Bg, int32_t env_offset, int32_t* obs, int32_t* gnn_assignment,
+                       float* gnn_clause_features, int32_t emit_every_step, float* reward, int32_t reward_cols,
+                       uint8_t* done, int32_t done_cols, uint8_t* solved, int32_t* num_unsatisfied,
+                       int32_t* episode_step, int32_t* newly_satisfied, int32_t B, void* stream) {
+    if (obs && (gnn_assignment || gnn_clause_features)) return MSAT_EINVAL;   // one kind of policy input per launch
+    return rollout_launch(plan, bank, P, state_in, state_out, actions, num_steps, rng_in, chain_out, Bg, env_offset,
+                          obs, gnn_assignment, gnn_clause_features, emit_every_step, reward, reward_cols, done,
+                          done_cols, solved, num_unsatisfied, episode_step, newly_satisfied, B, stream);
 }
 
 int msat_get_obs(const msat_plan* plan, const void* bank, int32_t P, const uint32_t* state, int32_t* obs, int32_t B,
@@ -243,6 +348,8 @@ int msat_rollout_step_host(const msat_plan* plan, const void* bank, int32_t P, u
     const Dims& d = plan->d;
     const size_t act_per_env = (size_t)d.A * (d.action_mode == 0 ? 1 : d.V);
     const size_t obs_per_env = (size_t)d.A * d.D;
+    const ResultBufs rb{reward_dev, reward_cols, done_dev, done_cols, solved_dev, num_unsatisfied_dev, episode_step_dev,
+                        reward_host, done_host, solved_host, num_unsatisfied_host, episode_step_host};
 
     // One slice [b0, b0 + bc) of the batch on stream `w`: actions in, fused step, results out.
     auto run_slice = [&](int b0, int bc, cudaStream_t w) -> int {
@@ -260,27 +367,7 @@ int msat_rollout_step_host(const msat_plan* plan, const void* bank, int32_t P, u
                                    num_unsatisfied_dev ? num_unsatisfied_dev + b0 : nullptr,
                                    episode_step_dev ? episode_step_dev + b0 : nullptr, bc, (void*)w);
         if (rc != MSAT_OK || bc == 0) return rc;
-        // device->host result copies; outputs that are adjacent in both address spaces (the Python layer
-        // carves them out of one device block and one pinned block) travel as ONE copy
-        struct Seg { const char* dev; char* host; size_t bytes; };
-        Seg seg[5];
-        int ns = 0;
-        auto add = [&](const void* dv, void* hs, size_t off, size_t bytes) {
-            if (dv && hs && bytes) seg[ns++] = Seg{static_cast<const char*>(dv) + off, static_cast<char*>(hs) + off, bytes};
-        };
-        add(reward_dev, reward_host, (size_t)b0 * reward_cols * sizeof(float), (size_t)bc * reward_cols * sizeof(float));
-        add(num_unsatisfied_dev, num_unsatisfied_host, (size_t)b0 * 4, (size_t)bc * 4);
-        add(episode_step_dev, episode_step_host, (size_t)b0 * 4, (size_t)bc * 4);
-        add(done_dev, done_host, (size_t)b0 * done_cols, (size_t)bc * done_cols);
-        add(solved_dev, solved_host, (size_t)b0, (size_t)bc);
-        for (int i = 1; i < ns; ++i)          // insertion sort by device address
-            for (int j = i; j > 0 && seg[j].dev < seg[j - 1].dev; --j) { Seg t = seg[j]; seg[j] = seg[j - 1]; seg[j - 1] = t; }
-        for (int i = 0; i < ns && e == cudaSuccess;) {
-            Seg cur = seg[i++];
-            while (i < ns && seg[i].dev == cur.dev + cur.bytes && seg[i].host == cur.host + cur.bytes) cur.bytes += seg[i++].bytes;
-            e = cudaMemcpyAsync(cur.host, cur.dev, cur.bytes, cudaMemcpyDeviceToHost, w);
-        }
-        return (int)e;
+        return (int)copy_results(rb, b0, bc, w);
     };
 
     constexpr int kSlices = 4;
@@ -291,26 +378,133 @@ int msat_rollout_step_host(const msat_plan* plan, const void* bank, int32_t P, u
     }
     // Large batch: slices alternate between two internal streams so that the action upload of slice
     // i+1 and the result download of slice i-1 overlap the kernel of slice i (separate copy engines).
+    int rc = MSAT_OK;
     {
-        std::lock_guard<std::mutex> lock(g_pipe.mu);
-        cudaError_t e = g_pipe.init();
+        std::lock_guard<std::mutex> lock(g_pipe_mu);
+        SyncPipe* pipe = nullptr;
+        cudaError_t e = sync_pipe_for_current_device(&pipe);
         if (e != cudaSuccess) return (int)e;
-        e = cudaEventRecord(g_pipe.fork, s);
-        for (int w = 0; w < 2 && e == cudaSuccess; ++w) e = cudaStreamWaitEvent(g_pipe.ws[w], g_pipe.fork, 0);
+        e = cudaEventRecord(pipe->fork, s);
+        for (int w = 0; w < 2 && e == cudaSuccess; ++w) e = cudaStreamWaitEvent(pipe->ws[w], pipe->fork, 0);
         if (e != cudaSuccess) return (int)e;
         const int per = (((B + kSlices - 1) / kSlices) + 63) & ~63;   // multiple of 64 envs keeps every slice aligned
-        for (int c = 0, b0 = 0; b0 < B; ++c, b0 += per) {
+        for (int c = 0, b0 = 0; b0 < B && rc == MSAT_OK; ++c, b0 += per) {
             const int bc = B - b0 < per ? B - b0 : per;
-            int rc = run_slice(b0, bc, g_pipe.ws[c & 1]);
-            if (rc != MSAT_OK) return rc;
+            rc = run_slice(b0, bc, pipe->ws[c & 1]);
         }
-        for (int w = 0; w < 2 && e == cudaSuccess; ++w) {
-            e = cudaEventRecord(g_pipe.join[w], g_pipe.ws[w]);
-            if (e == cudaSuccess) e = cudaStreamWaitEvent(s, g_pipe.join[w], 0);
+        // always join the internal streams back into the caller's stream -- also after a failed slice, so that
+        // nothing enqueued so far is still running when the caller sees the error
+        for (int w = 0; w < 2; ++w) {
+            cudaError_t j = cudaEventRecord(pipe->join[w], pipe->ws[w]);
+            if (j == cudaSuccess) j = cudaStreamWaitEvent(s, pipe->join[w], 0);
+            if (j != cudaSuccess && rc == MSAT_OK) rc = (int)j;
         }
-        if (e != cudaSuccess) return (int)e;
     }
-    return cuda_rc(cudaStreamSynchronize(s));
+    const cudaError_t se = cudaStreamSynchronize(s);
+    return rc != MSAT_OK ? rc : cuda_rc(se);
+}
+
+// ---- asynchronous host pipeline (double-buffered host I/O) -------------------------------------------------
+struct msat_host_pipe {
+    int dev = 0, depth = 0;
+    cudaStream_t s_in = nullptr, s_out = nullptr;
+    cudaEvent_t ev_h2d[kMaxPipeDepth] = {}, ev_kernel[kMaxPipeDepth] = {}, ev_d2h[kMaxPipeDepth] = {};
+    bool kernel_valid[kMaxPipeDepth] = {}, d2h_valid[kMaxPipeDepth] = {};
+};
+
+int msat_host_pipe_create(msat_host_pipe** out, int32_t depth) {
+    if (!out || depth < 1 || depth > kMaxPipeDepth) return MSAT_EINVAL;
+    *out = nullptr;
+    msat_host_pipe* p = new (std::nothrow) msat_host_pipe();
+    if (!p) return MSAT_EINVAL;
+    p->depth = depth;
+    cudaError_t e = cudaGetDevice(&p->dev);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&p->s_in, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&p->s_out, cudaStreamNonBlocking);
+    for (int i = 0; i < depth && e == cudaSuccess; ++i) {
+        e = cudaEventCreateWithFlags(&p->ev_h2d[i], cudaEventDisableTiming);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&p->ev_kernel[i], cudaEventDisableTiming);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&p->ev_d2h[i], cudaEventDisableTiming);
+    }
+    if (e != cudaSuccess) { msat_host_pipe_destroy(p); return (int)e; }
+    *out = p;
+    return MSAT_OK;
+}
+
+void msat_host_pipe_destroy(msat_host_pipe* p) {
+    if (!p) return;
+    if (p->s_in) cudaStreamSynchronize(p->s_in);
+    if (p->s_out) cudaStreamSynchronize(p->s_out);
+    for (int i = 0; i < kMaxPipeDepth; ++i) {
+        if (p->ev_h2d[i]) cudaEventDestroy(p->ev_h2d[i]);
+        if (p->ev_kernel[i]) cudaEventDestroy(p->ev_kernel[i]);
+        if (p->ev_d2h[i]) cudaEventDestroy(p->ev_d2h[i]);
+    }
+    if (p->s_in) cudaStreamDestroy(p->s_in);
+    if (p->s_out) cudaStreamDestroy(p->s_out);
+    delete p;
+}
+
+int msat_rollout_step_host_async(msat_host_pipe* pipe, int32_t slot, const msat_plan* plan, const void* bank,
+                                 int32_t P, uint32_t* state, const int32_t* actions_host, int32_t* actions_dev,
+                                 const uint32_t* rng_in, uint32_t* chain_out, int32_t Bg, int32_t env_offset,
+                                 int32_t* obs_dev, float* reward_dev, int32_t reward_cols, uint8_t* done_dev,
+                                 int32_t done_cols, uint8_t* solved_dev, int32_t* num_unsatisfied_dev,
+                                 int32_t* episode_step_dev, float* reward_host, uint8_t* done_host,
+                                 uint8_t* solved_host, int32_t* num_unsatisfied_host, int32_t* episode_step_host,
+                                 int32_t B, void* stream) {
+    if (!pipe || slot < 0 || slot >= pipe->depth || !plan || !actions_host || !actions_dev || B < 0) return MSAT_EINVAL;
+    cudaStream_t s = (cudaStream_t)stream;
+    const Dims& d = plan->d;
+    const size_t act_bytes = (size_t)B * d.A * (d.action_mode == 0 ? 1 : d.V) * sizeof(int32_t);
+    cudaError_t e = cudaSuccess;
+    // 1. upload this step's actions on the copy-in stream as soon as the kernel that last read this slot's
+    //    device staging buffer has finished (it overlaps the kernels of the steps in between)
+    if (pipe->kernel_valid[slot]) e = cudaStreamWaitEvent(pipe->s_in, pipe->ev_kernel[slot], 0);
+    if (e == cudaSuccess && act_bytes)
+        e = cudaMemcpyAsync(actions_dev, actions_host, act_bytes, cudaMemcpyHostToDevice, pipe->s_in);
+    if (e == cudaSuccess) e = cudaEventRecord(pipe->ev_h2d[slot], pipe->s_in);
+    // 2. the fused step on the caller's stream: after the upload, and after the previous download out of
+    //    this slot's device result buffers
+    if (e == cudaSuccess) e = cudaStreamWaitEvent(s, pipe->ev_h2d[slot], 0);
+    if (e == cudaSuccess && pipe->d2h_valid[slot]) e = cudaStreamWaitEvent(s, pipe->ev_d2h[slot], 0);
+    if (e != cudaSuccess) return (int)e;
+    int rc = msat_rollout_step(plan, bank, P, state, state, actions_dev, rng_in, chain_out, Bg, env_offset, obs_dev,
+                               reward_dev, reward_cols, done_dev, done_cols, solved_dev, num_unsatisfied_dev,
+                               episode_step_dev, B, stream);
+    if (rc != MSAT_OK) return rc;
+    e = cudaEventRecord(pipe->ev_kernel[slot], s);
+    pipe->kernel_valid[slot] = e == cudaSuccess;
+    // 3. results to the host on the copy-out stream; msat_host_wait(slot) blocks on ev_d2h
+    if (e == cudaSuccess) e = cudaStreamWaitEvent(pipe->s_out, pipe->ev_kernel[slot], 0);
+    if (e == cudaSuccess && B > 0) {
+        const ResultBufs rb{reward_dev, reward_cols, done_dev, done_cols, solved_dev, num_unsatisfied_dev,
+                            episode_step_dev, reward_host, done_host, solved_host, num_unsatisfied_host,
+                            episode_step_host};
+        e = copy_results(rb, 0, B, pipe->s_out);
+    }
+    if (e == cudaSuccess) e = cudaEventRecord(pipe->ev_d2h[slot], pipe->s_out);
+    pipe->d2h_valid[slot] = e == cudaSuccess;
+    return cuda_rc(e);
+}
+
+int msat_host_wait(msat_host_pipe* pipe, int32_t slot) {
+    if (!pipe || slot < 0 || slot >= pipe->depth) return MSAT_EINVAL;
+    if (!pipe->d2h_valid[slot]) return MSAT_OK;
+    return cuda_rc(cudaEventSynchronize(pipe->ev_d2h[slot]));
+}
+
+int msat_shutdown(void) {
+    std::lock_guard<std::mutex> lock(g_pipe_mu);
+    for (auto& kv : g_pipes) {
+        int cur = 0;
+        if (cudaGetDevice(&cur) == cudaSuccess && cudaSetDevice(kv.first) == cudaSuccess) {
+            kv.second.destroy();
+            cudaSetDevice(cur);
+        }
+    }
+    g_pipes.clear();
+    return MSAT_OK;
 }
 
 int msat_rng_chain(const uint32_t* rng_in, uint32_t* chain_out, void* stream) {

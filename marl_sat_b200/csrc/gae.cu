@@ -5,6 +5,8 @@
 
 namespace msat {
 
+int g_gae_force_plain = 0;   // msat_debug_option("gae_plain", 1): keep the register-chunked scan (A/B measurements)
+
 constexpr int GAE_CHUNK = 8;      // loads in flight per array and thread in the segmented scan
 constexpr int GAE_CHUNK_1 = 16;   // ... and in the plain (S = 1) scan, which has fewer warps per SM
 
@@ -100,6 +102,114 @@ __global__ void __launch_bounds__(32 * S) gae_kernel(const float* __restrict__ r
     }
 }
 
+// ---- software-pipelined plain scan (S = 1) ------------------------------------------------------------
+// When the batch alone fills the GPU (one thread per env column, ~14 warps per SM at 65,536 envs) the
+// limiter of the register-chunked scan above is latency: a warp's loads and its dependent chain do not
+// overlap.  Here every warp owns a private ring of GP_NS stages x GP_CH time steps in shared memory that
+// it fills with 16-byte cp.async (LDGSTS) copies -- reward / value rows of its 32 columns (128 B each) and
+// the done row (32 B) -- GP_NS-1 stages ahead of the chain, so ~7 KB per warp are in flight at any time
+// without holding registers.  No cross-warp synchronisation; the arithmetic is gae_segment's.
+constexpr int GP_CH = 8;                    // time steps per stage (multiple of 4, <= 16)
+constexpr int GP_NS = 4;                    // ring depth
+constexpr int GP_STAGE = GP_CH * (128 + 128 + 32);
+constexpr int GP_WARPS = 4;
+
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem_dst)), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+__global__ void __launch_bounds__(32 * GP_WARPS) gae_pipe_kernel(const float* __restrict__ reward, long long rs_t,
+                                                                 const uint8_t* __restrict__ done,
+                                                                 const float* __restrict__ value,
+                                                                 const float* __restrict__ last_val, float gamma,
+                                                                 float gl, float* __restrict__ adv,
+                                                                 float* __restrict__ targets, int T, int B,
+                                                                 double* __restrict__ stats) {
+    extern __shared__ __align__(16) uint8_t gp_smem[];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int b0 = (blockIdx.x * GP_WARPS + w) * 32;
+    if (b0 >= B) return;                                   // whole warp leaves
+    uint8_t* ring = gp_smem + (size_t)w * (GP_NS * GP_STAGE);
+    const int b = b0 + lane;
+    const bool ok = b < B;
+    const int nchunks = (T + GP_CH - 1) / GP_CH;
+
+    // chunk c = time steps T-1-c*GP_CH, ..., down to T-c*GP_CH-GP_CH (row i of the stage = step t_hi - i)
+    auto issue = [&](int c) {
+        if (c < nchunks) {
+            uint8_t* st = ring + (c % GP_NS) * GP_STAGE;
+            const int t_hi = T - 1 - c * GP_CH;
+            const int piece = lane & 7, col = b0 + piece * 4;
+#pragma unroll
+            for (int j = 0; j < GP_CH / 4; ++j) {
+                const int i = (lane >> 3) + 4 * j, t = t_hi - i;
+                if (t >= 0 && col < B) {
+                    cp_async16(st + i * 128 + piece * 16, reward + (long long)t * rs_t + col);
+                    cp_async16(st + GP_CH * 128 + i * 128 + piece * 16, value + (size_t)t * B + col);
+                }
+            }
+            const int i = lane >> 1, t = t_hi - i, dcol = b0 + (lane & 1) * 16;
+            if (i < GP_CH && t >= 0 && dcol < B)
+                cp_async16(st + GP_CH * 256 + i * 32 + (lane & 1) * 16, done + (size_t)t * B + dcol);
+        }
+        cp_async_commit();                                 // one group per call keeps the group count uniform
+    };
+
+#pragma unroll
+    for (int c = 0; c < GP_NS - 1; ++c) issue(c);
+    float next_value = ok ? __ldg(last_val + b) : 0.0f;
+    float gae = 0.0f;
+    double ssum = 0.0, ssq = 0.0;
+    for (int c = 0; c < nchunks; ++c) {
+        issue(c + GP_NS - 1);
+        cp_async_wait<GP_NS - 1>();                        // chunk c has landed (this thread's copies) ...
+        __syncwarp();                                      // ... and every other lane's
+        const uint8_t* st = ring + (c % GP_NS) * GP_STAGE;
+        const float* sr = reinterpret_cast<const float*>(st);
+        const float* sv = reinterpret_cast<const float*>(st + GP_CH * 128);
+        const uint8_t* sd = st + GP_CH * 256;
+        const int t_hi = T - 1 - c * GP_CH;
+        float r[GP_CH], v[GP_CH];
+        uint8_t dn[GP_CH];
+#pragma unroll
+        for (int i = 0; i < GP_CH; ++i) {
+            r[i] = sr[i * 32 + lane];
+            v[i] = sv[i * 32 + lane];
+            dn[i] = sd[i * 32 + lane];
+        }
+#pragma unroll
+        for (int i = 0; i < GP_CH; ++i) {
+            const int t = t_hi - i;
+            if (t >= 0 && ok) {
+                const float nt = dn[i] ? 0.0f : 1.0f;
+                const float cc = __fmul_rn(gl, nt);
+                const float delta = __fsub_rn(__fadd_rn(r[i], __fmul_rn(__fmul_rn(gamma, next_value), nt)), v[i]);
+                gae = __fadd_rn(delta, __fmul_rn(cc, gae));
+                ssum += (double)gae;
+                ssq += (double)gae * (double)gae;
+                __stcs(adv + (size_t)t * B + b, gae);
+                __stcs(targets + (size_t)t * B + b, __fadd_rn(gae, v[i]));        // learner:526
+                next_value = v[i];
+            }
+        }
+        __syncwarp();                                      // the stage is refilled by the next issue()
+    }
+    if (stats) {
+        for (int o = 16; o > 0; o >>= 1) {
+            ssum += __shfl_xor_sync(0xffffffffu, ssum, o);
+            ssq += __shfl_xor_sync(0xffffffffu, ssq, o);
+        }
+        if (lane == 0) {
+            atomicAdd(&stats[1], ssum);
+            atomicAdd(&stats[2], ssq);
+            if (blockIdx.x == 0 && w == 0) atomicAdd(&stats[0], (double)T * (double)B);
+        }
+    }
+}
+
 __global__ void __launch_bounds__(256) adv_stats_kernel(const float* __restrict__ adv, long long count,
                                                         double* __restrict__ stats) {
     double s = 0.0, ss = 0.0;
@@ -126,7 +236,11 @@ __global__ void __launch_bounds__(256) adv_stats_kernel(const float* __restrict_
     }
 }
 
-// adv = (adv - mean) / (std + 1e-8), population std over all elements (learner:530-532)
+// adv = (adv - mean) / (std + 1e-8), population std over all elements (learner:530-532).
+// 8 B per element of pure streaming: 16-byte accesses, four independent chunks per thread in flight,
+// grid sized by the element count; the <= 3 elements before the first 16-byte boundary and the tail
+// are handled by the first threads of block 0.
+constexpr int NORM_UNROLL = 4;
 __global__ void __launch_bounds__(256) adv_normalize_kernel(float* __restrict__ adv, long long count,
                                                             const double* __restrict__ stats) {
     const double n = stats[0];
@@ -135,9 +249,34 @@ __global__ void __launch_bounds__(256) adv_normalize_kernel(float* __restrict__ 
     var = var > 0.0 ? var : 0.0;
     const float fm = (float)mean;
     const float denom = __fadd_rn((float)sqrt(var), 1e-8f);
-    const long long stride = (long long)gridDim.x * blockDim.x;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += stride)
-        adv[i] = __fdiv_rn(__fsub_rn(adv[i], fm), denom);
+    const long long head = min(count, (long long)((16 - (reinterpret_cast<uintptr_t>(adv) & 15)) & 15) / 4);
+    const long long n4 = (count - head) / 4;
+    float4* a4 = reinterpret_cast<float4*>(adv + head);
+    const long long base = ((long long)blockIdx.x * blockDim.x) * NORM_UNROLL + threadIdx.x;
+    float4 x[NORM_UNROLL];
+#pragma unroll
+    for (int u = 0; u < NORM_UNROLL; ++u) {
+        const long long i = base + (long long)u * blockDim.x;
+        if (i < n4) x[u] = a4[i];
+    }
+#pragma unroll
+    for (int u = 0; u < NORM_UNROLL; ++u) {
+        const long long i = base + (long long)u * blockDim.x;
+        if (i < n4) {
+            float4 y;
+            y.x = __fdiv_rn(__fsub_rn(x[u].x, fm), denom);
+            y.y = __fdiv_rn(__fsub_rn(x[u].y, fm), denom);
+            y.z = __fdiv_rn(__fsub_rn(x[u].z, fm), denom);
+            y.w = __fdiv_rn(__fsub_rn(x[u].w, fm), denom);
+            a4[i] = y;
+        }
+    }
+    if (blockIdx.x == 0 && threadIdx.x < 8) {
+        const long long tail0 = head + 4 * n4;
+        const long long i = threadIdx.x < 4 ? (long long)threadIdx.x : tail0 + (threadIdx.x - 4);
+        const bool mine = threadIdx.x < 4 ? i < head : i < count;
+        if (mine) adv[i] = __fdiv_rn(__fsub_rn(adv[i], fm), denom);
+    }
 }
 
 cudaError_t launch_gae(const float* reward, long long rs_t, long long rs_b, const uint8_t* done, const float* value,
@@ -149,6 +288,16 @@ cudaError_t launch_gae(const float* reward, long long rs_t, long long rs_b, cons
     int S = 1;
     while (S < 32 && grid * S < 148 * 8 && T / (2 * S) >= GAE_CHUNK) S *= 2;
     const int seg_len = (T + S - 1) / S;
+    // the batch fills the GPU by itself and the rows are 16-byte copyable: pipelined plain scan
+    const bool rows16 = rs_b == 1 && (rs_t % 4) == 0 && (B % 16) == 0 &&
+                        ((reinterpret_cast<uintptr_t>(reward) | reinterpret_cast<uintptr_t>(value) |
+                          reinterpret_cast<uintptr_t>(done)) & 15) == 0;
+    if (S == 1 && rows16 && !g_gae_force_plain) {
+        const int pgrid = (B + 32 * GP_WARPS - 1) / (32 * GP_WARPS);
+        gae_pipe_kernel<<<pgrid, 32 * GP_WARPS, GP_WARPS * GP_NS * GP_STAGE, s>>>(reward, rs_t, done, value, last_val,
+                                                                                gamma, gl, adv, targets, T, B, stats);
+        return cudaGetLastError();
+    }
 #define MSAT_GAE_LAUNCH(SS)                                                                                         \
     gae_kernel<SS><<<grid, 32 * SS, 0, s>>>(reward, rs_t, rs_b, done, value, last_val, gamma, gl, adv, targets, T, B, \
                                             seg_len, stats)
@@ -173,9 +322,9 @@ cudaError_t launch_adv_stats(const float* adv, long long count, double* stats, c
 }
 cudaError_t launch_adv_normalize(float* adv, long long count, const double* stats, cudaStream_t s) {
     if (count == 0) return cudaSuccess;
-    long long blocks = (count + 256 * 8 - 1) / (256 * 8);
-    if (blocks > 148 * 8) blocks = 148 * 8;
-    if (blocks < 1) blocks = 1;
+    const long long per_block = 256LL * NORM_UNROLL * 4;
+    const long long blocks = (count + per_block - 1) / per_block + 1;     // +1: head/tail re-basing can shift by < 4
+    if (blocks > 0x7fffffffLL) return cudaErrorInvalidValue;
     adv_normalize_kernel<<<(int)blocks, 256, 0, s>>>(adv, count, stats);
     return cudaGetLastError();
 }

@@ -1,5 +1,7 @@
 // Private declarations shared by the translation units of libmarlsat_b200.so.
 #pragma once
+#include <atomic>
+
 #include "common.cuh"
 
 struct msat_plan {
@@ -10,30 +12,45 @@ struct msat_plan {
     int group_threads_noobs;   // GS used when a launch writes no observations (little per-env work: small groups)
     int smem_bytes_noobs;
     int compile_smem_bytes;
+    int reward_mode = 0;       // MSAT_REWARD_SPARSE / MSAT_REWARD_SHAPED (msat_plan_set_reward)
+    float r_gamma = 0.99f, r_clause = 0.02f, r_sat = 1.0f;
+    // devices on which the > 48 KB dynamic shared memory opt-in of the env kernels has been made (bit = device
+    // ordinal); set once per (plan, device) instead of once per launch
+    mutable std::atomic<unsigned long long> prepared_devices{0};
 };
 
 namespace msat {
 
 constexpr int kCtaThreads = 256;
+constexpr int kMaxSmemOptin = 227 * 1024;
 
-// Shared-memory carve-up of one env group (byte offsets from the group base).
+// Shared-memory carve-up of one env group (byte offsets from the group base).  Launches that write
+// observations stage the whole bank record (literals + agent-mask stream) and need the value / mask
+// re-basing buffers; launches without observations stage only the literal block and keep the per-clause
+// true-literal counts for the GNN features, so eight one-warp groups fit in ~26 KB per CTA.
 struct GroupLayout {
-    int rec, st, satw, x, smx, bar, misc, total;
+    int rec, st, satw, satw_old, x, smx, ntrue, bar, misc, total;
 };
-__host__ __device__ inline GroupLayout group_layout(const Dims& d) {
+__host__ __device__ inline GroupLayout group_layout(const Dims& d, bool obs) {
     GroupLayout L;
     int o = 0;
-    L.rec = o;  o += d.rec_bytes;                 // bank record (TMA destination, 128-byte aligned)
+    L.rec = o;  o += obs ? d.rec_bytes : ((d.lits_bytes + 127) & ~127);   // TMA destination, 128-byte aligned
     L.st = o;   o += 4 * d.state_words;           // state record (multiple of 16 bytes)
     L.satw = o; o += 4 * d.sw;
-    L.x = o;    o += 4 * d.xw;
+    L.satw_old = o; o += 4 * d.sw;                // clause status before the flips (shaped-reward mode only)
+    L.x = o;    o += obs ? 4 * d.xw : 0;
     o = (o + 7) & ~7;
-    L.smx = o;  o += 8 * (d.fw + 2);              // {mask word, value word} per 32 observation ints
+    L.smx = o;  o += obs ? 8 * (d.fw + 2) : 0;    // {mask word, value word} per 32 observation ints
+    L.ntrue = o; o += obs ? 0 : ((d.m + 3) & ~3); // true literals per clause (u8), GNN clause features
+    o = (o + 7) & ~7;
     L.bar = o;  o += 8;                           // mbarrier
-    L.misc = o; o += 16;                          // [0] #unsatisfied accumulator, [1] new problem idx, [2..3] reset key
+    L.misc = o; o += 16 + 64;                     // [0] #unsatisfied accumulator, [1] new problem idx, [2..3] reset key,
+                                                  // then float[16]: n_true / 3.0 table of the GNN clause features
     L.total = (o + 127) & ~127;
     return L;
 }
+
+constexpr int kMaxFusedSteps = 64;                // K of msat_rollout_steps
 
 struct EnvArgs {
     const uint8_t* bank;
@@ -58,9 +75,22 @@ struct EnvArgs {
     int32_t* num_unsat;
     int32_t* episode_step;
     int B;
+    // multi-step launches (msat_rollout_steps): K steps per env in one launch; step j reads
+    // actions + j * act_step_stride and writes row j of every [K, B, ...] output; observations / GNN
+    // inputs are written for every step (emit_every_step) or for the last one only
+    int num_steps;
+    long long act_step_stride;
+    int emit_every_step;
+    // reward: 0 = sparse solved reward (env:183-198); 1 = shaped reward of env:201-223
+    //   gamma * (-unsat') + unsat + r_clause * #newly satisfied + [solved] * r_sat
+    int reward_mode;
+    float r_gamma, r_clause, r_sat;
+    int32_t* newly_sat;         // optional int32[(K,) B]: clauses satisfied now that were not before the step
 };
 
 enum EnvMode { MODE_RESET = 0, MODE_STEP = 1, MODE_OBS = 2 };
+
+extern int g_gae_force_plain;   // gae.cu; msat_tune("gae_plain", 1)
 
 struct ExportArgs {
     const uint8_t* bank;

@@ -5,7 +5,7 @@
 namespace msat {
 
 // rng,act = split(rng); rng,step = split(rng); rng,prob,reset = split(rng,3)   (learner:397,416,426)
-__global__ void rng_chain_kernel(const uint32_t* __restrict__ rng_in, uint32_t* __restrict__ out) {
+__global__ void rng_chain_kernel(const uint32_t* rng_in, uint32_t* out) {   // may alias (read first)
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
     uint32_t out10[10];
     rng_chain_compute(rng_in[0], rng_in[1], out10);

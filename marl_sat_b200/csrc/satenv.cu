@@ -105,9 +105,10 @@ __device__ __forceinline__ bool clause_true_fixed(const uint16_t* lits, int m, i
     return sat;
 }
 
-template <int GS>
+// NT: also store the number of true literals per clause (u8) for the GNN clause features (learner:177-185).
+template <int GS, bool NT>
 __device__ __forceinline__ void eval_clauses(const Dims& d, const uint16_t* lits, const uint32_t* assign,
-                                             uint32_t* satw, int* nunsat, int gt) {
+                                             uint32_t* satw, uint8_t* ntrue, int* nunsat, int gt) {
     const int lane = gt & 31;
     int local = 0;
     for (int w = gt >> 5; w < d.sw; w += GS / 32) {
@@ -115,7 +116,21 @@ __device__ __forceinline__ void eval_clauses(const Dims& d, const uint16_t* lits
         const bool valid = c < d.m;
         bool sat = false;
         if (valid) {
-            if (d.k == 3) {
+            if (NT) {
+                int cnt = 0;
+                if (d.k == 3) {
+                    uint32_t code[3];
+#pragma unroll
+                    for (int j = 0; j < 3; ++j) code[j] = lits[lit_index(d.m, c, j)];
+#pragma unroll
+                    for (int j = 0; j < 3; ++j) cnt += literal_true(code[j], assign) ? 1 : 0;
+                } else {
+#pragma unroll 4
+                    for (int j = 0; j < d.k; ++j) cnt += literal_true(lits[lit_index(d.m, c, j)], assign) ? 1 : 0;
+                }
+                ntrue[c] = (uint8_t)cnt;
+                sat = cnt > 0;
+            } else if (d.k == 3) {
                 sat = clause_true_fixed<3>(lits, d.m, c, assign);
             } else {
 #pragma unroll 4
@@ -123,13 +138,12 @@ __device__ __forceinline__ void eval_clauses(const Dims& d, const uint16_t* lits
             }
         }
         const uint32_t word = __ballot_sync(0xffffffffu, valid && sat);
-        const uint32_t bad = __ballot_sync(0xffffffffu, valid && !sat);
         if (lane == 0) {
             satw[w] = word;
-            local += __popc(bad);
+            if (nunsat) local += min(32, d.m - w * 32) - __popc(word);
         }
     }
-    if (lane == 0 && local) atomicAdd(nunsat, local);
+    if (nunsat && lane == 0 && local) atomicAdd(nunsat, local);
 }
 
 // assign = randint(key, (n,), 0, 2) (env:162): bit 0 of threefry_2x32(split(key)[1], arange(n)).
@@ -199,7 +213,7 @@ __device__ __forceinline__ int4 expand_nibble(uint32_t mn, uint32_t xn) {
 // value is [assign | clause status | assign] repeated per agent.  Both streams are re-based to the
 // 128-byte aligned start of the range so every lane owns whole 16-byte chunks (st.global.cs.v4).
 template <int GS>
-__device__ __forceinline__ void emit_obs(const Dims& d, int e, const uint32_t* assign, const uint32_t* satw,
+__device__ __forceinline__ void emit_obs(const Dims& d, long long row, const uint32_t* assign, const uint32_t* satw,
                                          uint32_t* X, uint2* smx, const uint32_t* mflat,
                                          int32_t* __restrict__ obs, int gid, int gt) {
     for (int w = gt; w < d.xw; w += GS) {
@@ -209,7 +223,7 @@ __device__ __forceinline__ void emit_obs(const Dims& d, int e, const uint32_t* a
     }
     group_sync<GS>(gid);
 
-    const long long g_start = (long long)e * d.AD;
+    const long long g_start = row * d.AD;
     const int s = (int)(g_start & 31);
     const int nw = (s + d.AD + 31) >> 5;
     for (int w = gt; w < nw; w += GS) {
@@ -265,49 +279,113 @@ __device__ __forceinline__ void emit_obs(const Dims& d, int e, const uint32_t* a
     }
 }
 
-// Dynamic GNN input of the env's (post-reset) state straight from the shared-memory formula record
-// (learner:165-195): assignment int32[n]; clause_features float[m][3] = {is_sat, #true literals / 3.0, 1}.
-// Lets a GNN-style consumer skip the local observations altogether.
+// `count` 4-byte values f(0..count-1) to a 4-byte aligned destination with 16-byte streaming stores: the
+// (at most 3) elements before the first 16-byte boundary and after the last complete chunk go out as scalars.
+template <int GS, typename F>
+__device__ __forceinline__ void store_words_vec4(uint32_t* __restrict__ dst, int count, int gt, F f) {
+    int head = (int)(((16u - (uint32_t)(reinterpret_cast<uintptr_t>(dst) & 15u)) & 15u) >> 2);
+    head = head < count ? head : count;
+    const int n4 = (count - head) >> 2;
+    uint4* d4 = reinterpret_cast<uint4*>(dst + head);
+    for (int q = gt; q < n4; q += GS) {
+        const int i = head + 4 * q;
+        __stcs(d4 + q, make_uint4(f(i), f(i + 1), f(i + 2), f(i + 3)));
+    }
+    if (gt < head) dst[gt] = f(gt);
+    const int i = head + 4 * n4 + gt;
+    if (gt < 3 && i < count) dst[i] = f(i);
+}
+
+// Dynamic GNN input of the env's (post-reset) state straight from shared memory (learner:165-195):
+// assignment int32[n]; clause_features float[m][3] = {is_sat, #true literals / 3.0, 1} -- the literal 3.0 of
+// learner:185 for every clause width.  Lets a GNN-style consumer skip the local observations altogether
+// (SURVEY.md F8, section 8f rank 1).  `ntrue` holds the per-clause counts of the last evaluation; the
+// k+1 possible quotients are tabulated once per group (cf1), so the 3m floats leave as 16-byte stores.
 template <int GS>
-__device__ __forceinline__ void emit_gnn(const Dims& d, int e, const uint16_t* lits, const uint32_t* assign,
-                                         int32_t* __restrict__ gnn_assign, float* __restrict__ gnn_cf, int gt) {
+__device__ __forceinline__ void emit_gnn(const Dims& d, long long row, const uint8_t* ntrue, const float* cf1,
+                                         const uint32_t* assign, int32_t* __restrict__ gnn_assign,
+                                         float* __restrict__ gnn_cf, int gt) {
     if (gnn_assign)
-        for (int v = gt; v < d.n; v += GS) gnn_assign[(size_t)e * d.n + v] = (int)((assign[v >> 5] >> (v & 31)) & 1u);
+        store_words_vec4<GS>(reinterpret_cast<uint32_t*>(gnn_assign) + row * d.n, d.n, gt,
+                             [&](int v) { return (assign[v >> 5] >> (v & 31)) & 1u; });
     if (gnn_cf)
-        for (int c = gt; c < d.m; c += GS) {
-            int ntrue = 0;
-            for (int j = 0; j < d.k; ++j) ntrue += literal_true(lits[lit_index(d.m, c, j)], assign) ? 1 : 0;
-            float* o = gnn_cf + ((size_t)e * d.m + c) * 3;
-            o[0] = ntrue > 0 ? 1.0f : 0.0f;
-            o[1] = __fdiv_rn((float)ntrue, 3.0f);       // the literal 3.0 of learner:185 for every clause width
-            o[2] = 1.0f;
-        }
+        store_words_vec4<GS>(reinterpret_cast<uint32_t*>(gnn_cf) + row * d.m * 3, 3 * d.m, gt, [&](int i) {
+            const int c = (int)(((uint32_t)i * 43691u) >> 17);        // i / 3 for i < 98304
+            const int comp = i - 3 * c;
+            const int nt = ntrue[c];
+            const float v = comp == 0 ? (nt > 0 ? 1.0f : 0.0f)
+                                      : (comp == 1 ? (nt < 16 ? cf1[nt] : __fdiv_rn((float)nt, 3.0f)) : 1.0f);
+            return __float_as_uint(v);
+        });
+}
+
+// One rollout step of the rng alone (learner:397,416,426): rng <- split(rng)[0]; rng <- split(rng)[0];
+// rng <- split(rng, 3)[0].
+__device__ __forceinline__ void rng_advance(uint32_t& r0, uint32_t& r1) {
+    uint32_t a[2], b[2];
+    split2(r0, r1, a, b);
+    split2(a[0], a[1], a, b);
+    uint32_t x0 = 0u, x1 = 3u, y0 = 1u, y1 = 4u;
+    threefry2x32(a[0], a[1], x0, x1);
+    threefry2x32(a[0], a[1], y0, y1);
+    r0 = x0;
+    r1 = y0;
 }
 
 // =====================================================================================
-// K_env<GS, MODE>: reset / step (+ fused auto-reset) / get_obs.  256-thread CTAs, 256/GS envs each.
+// K_env<GS, MODE, OBS>: reset / step (+ fused auto-reset, + K fused steps) / get_obs.
+// 256-thread CTAs, 256/GS envs each.  OBS = the launch writes local observations (whole bank record
+// staged, observation re-basing buffers); !OBS = literal block only, optional GNN-input outputs.
 // =====================================================================================
-template <int GS, int MODE>
-__global__ void __launch_bounds__(kCtaThreads) env_kernel(const Dims d, const EnvArgs a) {
+template <int GS, int MODE, bool OBS, bool MULTI>
+__global__ void __launch_bounds__(kCtaThreads, MULTI ? 4 : 8) env_kernel(const Dims d, const EnvArgs a) {
     extern __shared__ __align__(128) uint8_t smem_raw[];
+    constexpr int NG = kCtaThreads / GS;
     const int gid = threadIdx.x / GS, gt = threadIdx.x % GS;
-    const int e = blockIdx.x * (kCtaThreads / GS) + gid;
+    const int e = blockIdx.x * NG + gid;
+    const GroupLayout L = group_layout(d, OBS);
+    const int K = MULTI ? a.num_steps : 1;          // MULTI only with MODE_STEP
+
+    // ---- K > 1 with fused keys: the K chains {rng', act, step, prob, reset} of learner:397-434, once per CTA
+    uint32_t* s_chain = reinterpret_cast<uint32_t*>(smem_raw + (size_t)NG * L.total);
+    if (MULTI && a.rng_in) {
+        if (threadIdx.x == 0) {
+            uint32_t r0 = a.rng_in[0], r1 = a.rng_in[1];
+            for (int j = 0; j < K; ++j) {          // the dependent part: three Threefry levels per step
+                s_chain[10 * j] = r0;
+                s_chain[10 * j + 1] = r1;
+                rng_advance(r0, r1);
+            }
+        }
+        __syncthreads();
+        if ((int)threadIdx.x < K) {
+            uint32_t c[10];
+            rng_chain_compute(s_chain[10 * threadIdx.x], s_chain[10 * threadIdx.x + 1], c);
+            for (int i = 0; i < 10; ++i) s_chain[10 * threadIdx.x + i] = c[i];
+        }
+        __syncthreads();
+        if (blockIdx.x == 0 && threadIdx.x < 10) a.chain_out[threadIdx.x] = s_chain[10 * (K - 1) + threadIdx.x];
+    }
     if (e >= a.B) return;   // whole group leaves together
 
-    const GroupLayout L = group_layout(d);
     uint8_t* base = smem_raw + (size_t)gid * L.total;
     uint8_t* rec = base + L.rec;
     uint32_t* st = reinterpret_cast<uint32_t*>(base + L.st);
     uint32_t* satw = reinterpret_cast<uint32_t*>(base + L.satw);
+    uint32_t* satw_old = reinterpret_cast<uint32_t*>(base + L.satw_old);
     uint32_t* X = reinterpret_cast<uint32_t*>(base + L.x);
     uint2* smx = reinterpret_cast<uint2*>(base + L.smx);
+    uint8_t* ntrue = base + L.ntrue;
     uint64_t* bar = reinterpret_cast<uint64_t*>(base + L.bar);
     int* misc = reinterpret_cast<int*>(base + L.misc);
     const uint16_t* lits = reinterpret_cast<const uint16_t*>(rec);
     const uint32_t* mflat = reinterpret_cast<const uint32_t*>(rec + d.lits_bytes);
     uint32_t* st_tail = st + d.aw;
+    const uint32_t tma_bytes = OBS ? (uint32_t)d.rec_bytes : (uint32_t)d.lits_bytes;
+    const bool want_gnn = !OBS && (a.gnn_assign || a.gnn_cf);
+    float* cf1 = reinterpret_cast<float*>(misc + 4);     // n_true / 3.0 for n_true = 0..15 (learner:185)
 
-    // ---- stage inputs: state record (plain loads) and bank record (TMA bulk copy) ----
+    // ---- stage the state record (plain loads) ----
     if (MODE == MODE_RESET) {
         for (int i = gt; i < d.state_words; i += GS) st[i] = 0u;
     } else {
@@ -318,152 +396,225 @@ __global__ void __launch_bounds__(kCtaThreads) env_kernel(const Dims d, const En
         misc[0] = 0;
         mbar_init(bar, 1);
     }
+    if (want_gnn && gt < 16) cf1[gt] = __fdiv_rn((float)gt, 3.0f);
     group_sync<GS>(gid);
 
-    // Every thread takes its copy of the scalar state fields NOW: thread 0 rewrites them in shared memory
-    // further down, and a warp that read `step` after that write would disagree with the others about
-    // `done` one step before the time-out and wait at a group barrier nobody else reaches.
-    const int step_old = (MODE == MODE_RESET) ? 0 : (int)st_tail[ST_STEP];
+    // Every thread keeps its own copy of the scalar state fields in registers from here on: thread 0 rewrites
+    // them in shared memory only after the last step, and a warp that read `step` from shared memory after
+    // such a write would disagree with the others about `done` and wait at a group barrier nobody else reaches.
+    int step_cur = (MODE == MODE_RESET) ? 0 : (int)st_tail[ST_STEP];
+    int nunsat_prev = (MODE == MODE_RESET) ? 0 : (int)st_tail[ST_NUNSAT];
+    uint32_t flags = (MODE == MODE_RESET) ? 0u : st_tail[ST_FLAGS];
     int pidx;
     if (MODE == MODE_RESET) pidx = a.prob_idx[e];
     else pidx = (int)st_tail[ST_PIDX];
     pidx = pidx < 0 ? 0 : (pidx >= a.P ? a.P - 1 : pidx);
-    if (gt == 0) {
-        mbar_expect_tx(bar, (uint32_t)d.rec_bytes);
-        tma_load_1d(rec, a.bank + (size_t)pidx * d.rec_bytes, (uint32_t)d.rec_bytes, bar);
-    }
+    int loaded_pidx = -1;
+    uint32_t phase = 0u;
+    int nunsat = nunsat_prev;
 
-    // ---- new assignment while the record is in flight ----
-    if (MODE == MODE_RESET) {
-        threefry_assign<GS>(d, a.keys[2 * (size_t)e], a.keys[2 * (size_t)e + 1], st, gt);
-    } else if (MODE == MODE_STEP) {
-        apply_actions<GS>(d, a.actions, e, st, gt);
-    }
-    group_sync<GS>(gid);
-    mbar_wait(bar, 0);
+    for (int j = 0; j < K; ++j) {
+        const bool last = j == K - 1;
+        const bool emit = last || a.emit_every_step;
+        const long long row = (a.emit_every_step ? (long long)j * a.B : 0LL) + e;     // row of obs / GNN outputs
+        const long long orow = (long long)j * a.B + e;                                  // row of reward / done / info
 
-    eval_clauses<GS>(d, lits, st, satw, &misc[0], gt);
-    group_sync<GS>(gid);
-    int nunsat = misc[0];
-
-    if (MODE == MODE_STEP) {
-        if (a.rng_in && blockIdx.x == 0 && threadIdx.x == 0) {
-            // advance the rollout rng once per step (learner:397,416,426); chain_out never aliases rng_in
-            uint32_t c[10];
-            rng_chain_compute(a.rng_in[0], a.rng_in[1], c);
-            for (int i = 0; i < 10; ++i) a.chain_out[i] = c[i];
+        // ---- formula record: TMA bulk copy unless the env's formula is already staged ----
+        if (loaded_pidx != pidx && gt == 0) {
+            if (j > 0) fence_proxy_async();
+            mbar_expect_tx(bar, tma_bytes);
+            tma_load_1d(rec, a.bank + (size_t)pidx * d.rec_bytes, tma_bytes, bar);
         }
-        const bool solved = nunsat == 0;                                  // env:257
-        const bool done = solved || (step_old + 1 >= d.max_steps);        // env:258-259
-        // pre-reset outputs stored in the Transition (learner:467-478)
-        if (a.reward)
-            for (int i = gt; i < a.reward_cols; i += GS)
-                a.reward[(size_t)e * a.reward_cols + i] = solved ? 1.0f : 0.0f;                     // env:193
-        if (a.done)
-            for (int i = gt; i < a.done_cols; i += GS) a.done[(size_t)e * a.done_cols + i] = done ? 1 : 0;
-        if (gt == 0) {
-            if (a.solved) a.solved[e] = solved ? 1 : 0;
-            if (a.num_unsat) a.num_unsat[e] = nunsat;
-            if (a.episode_step) a.episode_step[e] = step_old + 1;        // env:281
+        if (MODE == MODE_STEP && a.reward_mode) {
+            // shaped reward (env:201-223): clause status of the state BEFORE the flips
+            if (loaded_pidx != pidx) {
+                mbar_wait(bar, phase);
+                phase ^= 1u;
+                loaded_pidx = pidx;
+            }
+            eval_clauses<GS, false>(d, lits, st, satw_old, nullptr, nullptr, gt);
+            group_sync<GS>(gid);
         }
-        if (done && a.auto_reset) {
-            // learner:425-464: swap in a fresh episode on a newly drawn formula (group-uniform branch)
-            group_sync<GS>(gid);   // everyone is done reading the old record / misc
-            uint32_t rk0, rk1;
-            if (a.rng_in) {
-                // fused key derivation (learner:426-434) from the rollout rng, global env index
-                if (gt == 0) {
-                    uint32_t c[10], k[2];
-                    rng_chain_compute(a.rng_in[0], a.rng_in[1], c);
-                    misc[1] = (int)env_problem_index(c[6], c[7], a.Bg, a.env_off + (uint32_t)e, (uint32_t)a.P);
-                    env_reset_key(c[8], c[9], a.Bg, a.env_off + (uint32_t)e, k);
-                    misc[2] = (int)k[0];
-                    misc[3] = (int)k[1];
+
+        // ---- new assignment while the record is in flight ----
+        if (MODE == MODE_RESET) {
+            threefry_assign<GS>(d, a.keys[2 * (size_t)e], a.keys[2 * (size_t)e + 1], st, gt);
+        } else if (MODE == MODE_STEP) {
+            apply_actions<GS>(d, a.actions + (long long)j * a.act_step_stride, e, st, gt);
+        }
+        group_sync<GS>(gid);
+        if (loaded_pidx != pidx) {
+            mbar_wait(bar, phase);
+            phase ^= 1u;
+            loaded_pidx = pidx;
+        }
+
+        eval_clauses<GS, !OBS>(d, lits, st, satw, ntrue, &misc[0], gt);
+        group_sync<GS>(gid);
+        nunsat = misc[0];
+
+        if (MODE == MODE_STEP) {
+            if (!MULTI && a.rng_in && blockIdx.x == 0 && threadIdx.x == 0) {
+                // advance the rollout rng once per step (learner:397,416,426); chain_out never aliases rng_in
+                uint32_t c[10];
+                rng_chain_compute(a.rng_in[0], a.rng_in[1], c);
+                for (int i = 0; i < 10; ++i) a.chain_out[i] = c[i];
+            }
+            const bool solved = nunsat == 0;                                  // env:257
+            const bool done = solved || (step_cur + 1 >= d.max_steps);        // env:258-259
+            // pre-reset outputs stored in the Transition (learner:467-478)
+            int newly = 0;
+            float r = solved ? 1.0f : 0.0f;                                   // env:193
+            if (a.reward_mode) {
+                for (int w = 0; w < d.sw; ++w) newly += __popc(satw[w] & ~satw_old[w]);
+                // env:207-221, f32 with one rounding per operation
+                const float r_pbrs = __fsub_rn(__fmul_rn(a.r_gamma, (float)(-nunsat)), (float)(-nunsat_prev));
+                const float r_cl = __fmul_rn((float)newly, a.r_clause);
+                r = __fadd_rn(__fadd_rn(r_pbrs, r_cl), solved ? a.r_sat : 0.0f);
+            }
+            if (a.reward)
+                for (int i = gt; i < a.reward_cols; i += GS) a.reward[orow * a.reward_cols + i] = r;
+            if (a.done)
+                for (int i = gt; i < a.done_cols; i += GS) a.done[orow * a.done_cols + i] = done ? 1 : 0;
+            if (gt == 0) {
+                if (a.solved) a.solved[orow] = solved ? 1 : 0;
+                if (a.num_unsat) a.num_unsat[orow] = nunsat;
+                if (a.episode_step) a.episode_step[orow] = step_cur + 1;     // env:281
+                if (a.newly_sat) a.newly_sat[orow] = newly;
+            }
+            if (done && a.auto_reset) {
+                // learner:425-464: swap in a fresh episode on a newly drawn formula (group-uniform branch)
+                group_sync<GS>(gid);   // everyone is done reading the old record / misc
+                uint32_t rk0, rk1;
+                if (a.rng_in) {
+                    // fused key derivation (learner:426-434) from the rollout rng, global env index
+                    if (gt == 0) {
+                        uint32_t c[10], k[2];
+                        if (MULTI) {
+                            for (int i = 6; i < 10; ++i) c[i] = s_chain[10 * j + i];
+                        } else {
+                            rng_chain_compute(a.rng_in[0], a.rng_in[1], c);
+                        }
+                        misc[1] = (int)env_problem_index(c[6], c[7], a.Bg, a.env_off + (uint32_t)e, (uint32_t)a.P);
+                        env_reset_key(c[8], c[9], a.Bg, a.env_off + (uint32_t)e, k);
+                        misc[2] = (int)k[0];
+                        misc[3] = (int)k[1];
+                    }
+                    group_sync<GS>(gid);
+                    pidx = misc[1];
+                    rk0 = (uint32_t)misc[2];
+                    rk1 = (uint32_t)misc[3];
+                } else {
+                    pidx = a.prob_idx[e];
+                    rk0 = a.keys[2 * (size_t)e];
+                    rk1 = a.keys[2 * (size_t)e + 1];
                 }
+                pidx = pidx < 0 ? 0 : (pidx >= a.P ? a.P - 1 : pidx);
+                if (gt == 0) {
+                    misc[0] = 0;
+                    if (pidx != loaded_pidx) {
+                        fence_proxy_async();
+                        mbar_expect_tx(bar, tma_bytes);
+                        tma_load_1d(rec, a.bank + (size_t)pidx * d.rec_bytes, tma_bytes, bar);
+                    }
+                }
+                for (int i = gt; i < d.aw; i += GS) st[i] = 0u;
                 group_sync<GS>(gid);
-                pidx = misc[1];
-                rk0 = (uint32_t)misc[2];
-                rk1 = (uint32_t)misc[3];
+                threefry_assign<GS>(d, rk0, rk1, st, gt);
+                group_sync<GS>(gid);
+                if (pidx != loaded_pidx) {
+                    mbar_wait(bar, phase);
+                    phase ^= 1u;
+                    loaded_pidx = pidx;
+                }
+                eval_clauses<GS, !OBS>(d, lits, st, satw, ntrue, &misc[0], gt);
+                group_sync<GS>(gid);
+                nunsat = misc[0];
+                step_cur = 0;
+                flags = 0u;
             } else {
-                pidx = a.prob_idx[e];
-                rk0 = a.keys[2 * (size_t)e];
-                rk1 = a.keys[2 * (size_t)e + 1];
+                step_cur += 1;                                               // env:269
+                flags = done ? 1u : 0u;                                      // env:270
             }
-            pidx = pidx < 0 ? 0 : (pidx >= a.P ? a.P - 1 : pidx);
-            if (gt == 0) {
-                misc[0] = 0;
-                fence_proxy_async();
-                mbar_expect_tx(bar, (uint32_t)d.rec_bytes);
-                tma_load_1d(rec, a.bank + (size_t)pidx * d.rec_bytes, (uint32_t)d.rec_bytes, bar);
-            }
-            for (int i = gt; i < d.aw; i += GS) st[i] = 0u;
-            group_sync<GS>(gid);
-            threefry_assign<GS>(d, rk0, rk1, st, gt);
-            group_sync<GS>(gid);
-            mbar_wait(bar, 1);
-            eval_clauses<GS>(d, lits, st, satw, &misc[0], gt);
-            group_sync<GS>(gid);
-            nunsat = misc[0];
-            if (gt == 0) {
-                st_tail[ST_STEP] = 0u;
-                st_tail[ST_PIDX] = (uint32_t)pidx;
-                st_tail[ST_NUNSAT] = (uint32_t)nunsat;
-                st_tail[ST_FLAGS] = 0u;
-            }
-        } else if (gt == 0) {
-            st_tail[ST_STEP] = (uint32_t)(step_old + 1);                 // env:269
-            st_tail[ST_NUNSAT] = (uint32_t)nunsat;
-            st_tail[ST_FLAGS] = done ? 1u : 0u;                          // env:270
+            nunsat_prev = nunsat;
         }
-    } else if (MODE == MODE_RESET) {
+        if (emit) {
+            if (want_gnn) emit_gnn<GS>(d, row, ntrue, cf1, st, a.gnn_assign, a.gnn_cf, gt);
+            if (OBS && a.obs) emit_obs<GS>(d, row, st, satw, X, smx, mflat, a.obs, gid, gt);
+        }
+        if (!last) {
+            group_sync<GS>(gid);           // every lane has read misc[0] / the state of this step
+            if (gt == 0) misc[0] = 0;      // published by the barrier after the next step's flips
+        }
+    }
+
+    if (MODE != MODE_OBS) {
+        group_sync<GS>(gid);
         if (gt == 0) {
-            st_tail[ST_STEP] = 0u;                                       // env:170
+            st_tail[ST_STEP] = (uint32_t)step_cur;                           // env:170,269
             st_tail[ST_PIDX] = (uint32_t)pidx;
             st_tail[ST_NUNSAT] = (uint32_t)nunsat;
-            st_tail[ST_FLAGS] = 0u;                                      // env:171
+            st_tail[ST_FLAGS] = flags;                                       // env:171,270
         }
-    }
-    if (MODE != MODE_OBS) {
         group_sync<GS>(gid);
         uint32_t* sout = a.state_out + (size_t)e * d.state_words;
         for (int i = gt; i < d.state_words; i += GS) sout[i] = st[i];
     }
-    if (a.gnn_assign || a.gnn_cf) emit_gnn<GS>(d, e, lits, st, a.gnn_assign, a.gnn_cf, gt);
-    if (a.obs) emit_obs<GS>(d, e, st, satw, X, smx, mflat, a.obs, gid, gt);
 }
 
-template <int GS>
+template <int GS, bool OBS>
 static cudaError_t launch_env_gs(const msat_plan* plan, EnvMode mode, const EnvArgs& a, cudaStream_t s, int smem_bytes) {
     const int groups = kCtaThreads / GS;
     const int grid = (a.B + groups - 1) / groups;
     if (grid == 0) return cudaSuccess;
-    const void* fn = nullptr;
-    switch (mode) {
-        case MODE_RESET: fn = (const void*)env_kernel<GS, MODE_RESET>; break;
-        case MODE_STEP: fn = (const void*)env_kernel<GS, MODE_STEP>; break;
-        default: fn = (const void*)env_kernel<GS, MODE_OBS>; break;
-    }
+    const void* fns[4] = {(const void*)env_kernel<GS, MODE_RESET, OBS, false>,
+                          (const void*)env_kernel<GS, MODE_STEP, OBS, false>,
+                          (const void*)env_kernel<GS, MODE_OBS, OBS, false>,
+                          (const void*)env_kernel<GS, MODE_STEP, OBS, true>};
+    const bool multi = mode == MODE_STEP && a.num_steps > 1;
+    if (multi) smem_bytes += 40 * a.num_steps;
     if (smem_bytes > 48 * 1024) {
-        cudaError_t err = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
+        // opt in to > 48 KB of dynamic shared memory once per (plan, device), not once per launch
+        int dev = 0;
+        cudaError_t err = cudaGetDevice(&dev);
         if (err != cudaSuccess) return err;
+        const unsigned long long bit = 1ULL << ((OBS ? 0 : 32) + (dev & 31));
+        if (!(plan->prepared_devices.load(std::memory_order_acquire) & bit)) {
+            for (const void* f : fns) {
+                err = cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmemOptin);
+                if (err != cudaSuccess) return err;
+            }
+            plan->prepared_devices.fetch_or(bit, std::memory_order_release);
+        }
     }
+    const void* fn = fns[multi ? 3 : (mode == MODE_RESET ? 0 : (mode == MODE_STEP ? 1 : 2))];
     Dims d = plan->d;
     EnvArgs args = a;
     void* params[] = {&d, &args};
     return cudaLaunchKernel(fn, dim3(grid), dim3(kCtaThreads), params, (size_t)smem_bytes, s);
 }
 
-cudaError_t launch_env(const msat_plan* plan, EnvMode mode, const EnvArgs& a, cudaStream_t s) {
+cudaError_t launch_env(const msat_plan* plan, EnvMode mode, const EnvArgs& a0, cudaStream_t s) {
     // the group size follows the work per env: observation-writing launches use the plan's GS, launches
     // without observations the small-group variant
+    EnvArgs a = a0;
+    if (a.num_steps < 1) a.num_steps = 1;
     const bool noobs = a.obs == nullptr;
     const int gs = noobs ? plan->group_threads_noobs : plan->group_threads;
     const int smem = noobs ? plan->smem_bytes_noobs : plan->smem_bytes;
+    if (noobs) {
+        switch (gs) {
+            case 32: return launch_env_gs<32, false>(plan, mode, a, s, smem);
+            case 64: return launch_env_gs<64, false>(plan, mode, a, s, smem);
+            case 128: return launch_env_gs<128, false>(plan, mode, a, s, smem);
+            default: return launch_env_gs<256, false>(plan, mode, a, s, smem);
+        }
+    }
     switch (gs) {
-        case 32: return launch_env_gs<32>(plan, mode, a, s, smem);
-        case 64: return launch_env_gs<64>(plan, mode, a, s, smem);
-        case 128: return launch_env_gs<128>(plan, mode, a, s, smem);
-        default: return launch_env_gs<256>(plan, mode, a, s, smem);
+        case 32: return launch_env_gs<32, true>(plan, mode, a, s, smem);
+        case 64: return launch_env_gs<64, true>(plan, mode, a, s, smem);
+        case 128: return launch_env_gs<128, true>(plan, mode, a, s, smem);
+        default: return launch_env_gs<256, true>(plan, mode, a, s, smem);
     }
 }
 

@@ -86,12 +86,14 @@ def create_agent_groups(num_vars: int, vars_per_agent: Optional[int], verbose: b
 class _Plan:
     """RAII holder of an ``msat_plan*``."""
 
-    def __init__(self, n, m, k, A, action_mode, max_steps, group_threads=0):
+    def __init__(self, n, m, k, A, action_mode, max_steps, group_threads=0, reward=None):
         self._lib = _lib.load()
         h = C.c_void_p()
         _lib.check(self._lib.msat_plan_create(C.byref(h), n, m, k, A, action_mode, max_steps, group_threads),
                    "msat_plan_create")
         self.handle = h
+        if reward is not None:      # (mode, gamma, r_clause, r_sat)
+            _lib.check(self._lib.msat_plan_set_reward(h, *reward), "msat_plan_set_reward")
         self.dims = _lib.Dims()
         _lib.check(self._lib.msat_plan_dims(h, C.byref(self.dims)), "msat_plan_dims")
 
@@ -198,7 +200,7 @@ class SATEnv:
     def __init__(self, num_vars, num_clauses, max_steps: int, vars_per_agent: Optional[int] = None,
                  action_mode: int = 0, r_clause: float = 0.02, r_sat: float = 1.0, gamma: float = 0.99,
                  *, device: Union[str, torch.device, None] = None, verbose: bool = True,
-                 group_threads: int = 0):
+                 group_threads: int = 0, reward_mode: str = "sparse"):
         self._lib = _lib.load()
         self.num_vars = int(num_vars)
         self.num_clauses = int(num_clauses)
@@ -206,7 +208,12 @@ class SATEnv:
         self.agents = list(self.agent_groups.keys())
         self.num_agents = len(self.agents)
         self.agent_to_idx = {a: i for i, a in enumerate(self.agents)}
-        self.r_clause, self.r_sat, self.gamma = r_clause, r_sat, gamma      # stored, unused (env:40-42,183-198)
+        # stored but unused by the reference's active reward (env:40-42,183-198); reward_mode="shaped" selects
+        # the alternative team reward the reference keeps commented out (env:201-223), which does use them
+        self.r_clause, self.r_sat, self.gamma = r_clause, r_sat, gamma
+        if reward_mode not in ("sparse", "shaped"):
+            raise ValueError("reward_mode must be 'sparse' or 'shaped'")
+        self.reward_mode = reward_mode
         self.action_mode = int(action_mode)
         self.max_steps = int(max_steps)
         self.max_vars_per_agent = max(len(v) for v in self.agent_groups.values())
@@ -249,8 +256,9 @@ class SATEnv:
 
     def _plan_for(self, k: int) -> _Plan:
         if k not in self._plans:
+            reward = (1, float(self.gamma), float(self.r_clause), float(self.r_sat)) if self.reward_mode == "shaped" else None
             self._plans[k] = _Plan(self.num_vars, self.num_clauses, k, self.num_agents, self.action_mode,
-                                   self.max_steps, self._group_threads)
+                                   self.max_steps, self._group_threads, reward)
         return self._plans[k]
 
     def make_bank(self, clauses: ArrayLike, validate: bool = True) -> FormulaBank:
@@ -287,12 +295,18 @@ class SATEnv:
 
     def reset_from_bank(self, bank: FormulaBank, problem_idx: torch.Tensor, keys: torch.Tensor,
                         state_out: Optional[torch.Tensor] = None, obs_out: Optional[torch.Tensor] = None,
-                        want_obs: bool = True) -> Tuple[Optional[torch.Tensor], SATState]:
-        """Batched reset on formulas already resident in a bank: obs ``int32[B,A,D]`` + state."""
+                        want_obs: bool = True, validate_indices: bool = False) -> Tuple[Optional[torch.Tensor], SATState]:
+        """Batched reset on formulas already resident in a bank: obs ``int32[B,A,D]`` + state.
+        The kernels clamp a problem index into ``[0, P)``; ``validate_indices=True`` checks the range on the
+        host first (one device->host sync) and raises instead."""
         dev = self._require_cuda()
         d = bank.plan.dims
         B = int(problem_idx.shape[0])
         problem_idx = problem_idx.to(device=dev, dtype=torch.int32).contiguous()
+        if validate_indices and B:
+            lo, hi = int(problem_idx.min()), int(problem_idx.max())
+            if lo < 0 or hi >= bank.num_problems:
+                raise IndexError(f"problem_idx out of range [0, {bank.num_problems}): min {lo}, max {hi}")
         keys = as_u32_tensor(keys, dev)
         packed = state_out if state_out is not None else torch.empty((B, d.state_words), dtype=torch.int32, device=dev)
         obs = obs_out
@@ -333,6 +347,8 @@ class SATEnv:
         dones["__all__"] = sq(done_b[:, self.num_agents])                                # env:261
         infos = {"solved": sq(out["solved"].bool()), "num_unsatisfied": sq(out["num_unsatisfied"]),
                  "episode_step": sq(out["episode_step"])}                                # env:278-282
+        if out["newly_satisfied"] is not None:
+            infos["newly_satisfied"] = sq(out["newly_satisfied"])                         # env:211 (shaped reward only)
         return self._obs_dict(out["obs"], b), nxt, rewards, dones, infos
 
     def step(self, key, state, actions):
@@ -358,8 +374,13 @@ class SATEnv:
             block = torch.empty(B * (4 * rc + 8 + dc + 1), dtype=torch.uint8, device=dev)
             obs = torch.empty((B, A, D), dtype=torch.int32, device=dev) if want_obs else None
         o0, o1, o2, o3 = 4 * rc * B, 4 * rc * B + 4 * B, 4 * rc * B + 8 * B, 4 * rc * B + 8 * B + dc * B
+        newly = None
+        if self.reward_mode == "shaped":
+            newly = (torch.empty(B, dtype=torch.int32, pin_memory=True) if pinned_host
+                     else torch.empty(B, dtype=torch.int32, device=self._require_cuda()))
         return {
             "obs": obs,
+            "newly_satisfied": newly,
             "reward": block[:o0].view(torch.float32).view(B, rc),
             "num_unsatisfied": block[o0:o1].view(torch.int32),
             "episode_step": block[o1:o2].view(torch.int32),
@@ -379,8 +400,8 @@ class SATEnv:
             1 if auto_reset else 0, _ptr(new_problem_idx), _ptr(reset_keys),
             _ptr(out.get("obs")), _ptr(reward), int(reward.shape[-1]) if reward is not None else 0,
             _ptr(done), int(done.shape[-1]) if done is not None else 0, _ptr(out.get("solved")),
-            _ptr(out.get("num_unsatisfied")), _ptr(out.get("episode_step")), B, _stream_ptr(state_in.device)),
-            "msat_step")
+            _ptr(out.get("num_unsatisfied")), _ptr(out.get("episode_step")), _ptr(out.get("newly_satisfied")), B,
+            _stream_ptr(state_in.device)), "msat_step")
 
     # ------------------------------------------------------------------ observations
     def get_obs_array(self, state: SATState) -> torch.Tensor:

@@ -25,9 +25,23 @@ def calculate_gae(reward: torch.Tensor, done: torch.Tensor, value: torch.Tensor,
     lib = _lib.load()
     if not reward.is_cuda:
         raise RuntimeError("calculate_gae needs CUDA tensors: there is no CPU fallback")
+    if value.dim() != 2:
+        raise ValueError(f"value must be [T, B], got {tuple(value.shape)}")
     T, B = value.shape
     if reward.dtype != torch.float32 or value.dtype != torch.float32 or last_val.dtype != torch.float32:
         raise TypeError("reward/value/last_val must be float32")
+    if reward.dim() not in (2, 3) or tuple(reward.shape[:2]) != (T, B):
+        raise ValueError(f"reward must be [T, B] or [T, B, A] with T, B = {T}, {B}; got {tuple(reward.shape)}")
+    if tuple(done.shape) != (T, B) or done.dtype not in (torch.bool, torch.uint8):
+        raise ValueError(f"done must be bool/uint8 [T, B] = [{T}, {B}], got {done.dtype} {tuple(done.shape)}")
+    if tuple(last_val.shape) != (B,):
+        raise ValueError(f"last_val must be [B] = [{B}], got {tuple(last_val.shape)}")
+    for name, t in (("done", done), ("value", value), ("last_val", last_val)):
+        if t.device != reward.device:
+            raise ValueError(f"{name} is on {t.device}, reward on {reward.device}")
+    if stats is not None and (stats.dtype != torch.float64 or stats.numel() != 3 or stats.device != reward.device
+                              or not stats.is_contiguous()):
+        raise ValueError("stats must be a contiguous float64[3] tensor on the same device (zero it before the call)")
     if done.dtype == torch.bool:
         done = done.view(torch.uint8)
     done = done.contiguous()
@@ -56,11 +70,15 @@ def normalize_advantages(adv: torch.Tensor, stats: Optional[torch.Tensor] = None
     ``stats``: the local (count, sum, sum of squares) if ``calculate_gae`` already produced them (saves a
     pass over ``adv``); with ``torch.distributed`` initialised they are all-reduced first (a private copy)."""
     lib = _lib.load()
-    adv = adv if adv.is_contiguous() else adv.contiguous()
-    stats = advantage_stats(adv) if stats is None else stats.clone()
+    if stats is not None and (stats.dtype != torch.float64 or stats.numel() != 3):
+        raise ValueError("stats must be float64[3]")
+    work = adv if adv.is_contiguous() else adv.contiguous()      # a strided view is normalised through a copy ...
+    stats = advantage_stats(work) if stats is None else stats.clone()
     if torch.distributed.is_available() and torch.distributed.is_initialized() and \
             torch.distributed.get_world_size(group) > 1:
         torch.distributed.all_reduce(stats, op=torch.distributed.ReduceOp.SUM, group=group)
-    _lib.check(lib.msat_adv_normalize(_ptr(adv), adv.numel(), _ptr(stats), _stream_ptr(adv.device)),
+    _lib.check(lib.msat_adv_normalize(_ptr(work), work.numel(), _ptr(stats), _stream_ptr(work.device)),
                "msat_adv_normalize")
+    if work is not adv:
+        adv.copy_(work)                                          # ... and written back: the call is in place
     return adv

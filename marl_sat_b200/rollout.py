@@ -20,6 +20,7 @@ values of the single-device run.
 """
 from __future__ import annotations
 
+import ctypes as C
 from typing import Dict, Optional
 
 import torch
@@ -214,6 +215,55 @@ class VecSATEnv:
         self.keys._cur = 1 - cur
         return self.out
 
+    # ------------------------------------------------------------------ K fused steps
+    def alloc_multi_step_outputs(self, num_steps: int, emit_every_step: bool = False) -> Dict[str, torch.Tensor]:
+        """Output buffers of ``steps``: reward / done / info rows ``[K, B, ...]``; the policy input (local
+        observations or, with ``gnn_outputs``, the dynamic GNN input) for every step or for the final state."""
+        env, dev, B, K = self.env, self.state.device, self.num_envs, int(num_steps)
+        d = self.bank.plan.dims
+        rc, dc = int(self.out["reward"].shape[-1]), int(self.out["done"].shape[-1])
+        lead = (K, B) if emit_every_step else (B,)
+        out = {"reward": torch.empty((K, B, rc), dtype=torch.float32, device=dev),
+               "done": torch.empty((K, B, dc), dtype=torch.uint8, device=dev),
+               "solved": torch.empty((K, B), dtype=torch.uint8, device=dev),
+               "num_unsatisfied": torch.empty((K, B), dtype=torch.int32, device=dev),
+               "episode_step": torch.empty((K, B), dtype=torch.int32, device=dev),
+               "newly_satisfied": (torch.empty((K, B), dtype=torch.int32, device=dev)
+                                   if env.reward_mode == "shaped" else None),
+               "obs": None, "gnn_assignment": None, "gnn_clause_features": None,
+               "emit_every_step": bool(emit_every_step)}
+        if self.gnn_outputs:
+            out["gnn_assignment"] = torch.empty(lead + (d.n,), dtype=torch.int32, device=dev)
+            out["gnn_clause_features"] = torch.empty(lead + (d.m, 3), dtype=torch.float32, device=dev)
+        elif self.out.get("obs") is not None:
+            out["obs"] = torch.empty(lead + (d.A, d.D), dtype=torch.int32, device=dev)
+        return out
+
+    def steps(self, actions: torch.Tensor, out: Dict[str, torch.Tensor]) -> Dict[str, torch.Tensor]:
+        """K rollout steps in ONE launch (``msat_rollout_steps``) for an action table ``[K, B, A(, V)]`` that
+        does not depend on the intermediate observations (replay, open-loop evaluation, launch-bound small
+        batches).  Identical results to K calls of ``step``; ``out`` from ``alloc_multi_step_outputs``."""
+        K = int(actions.shape[0])
+        done, reward = out["done"], out["reward"]
+        _lib.check(self.env._lib.msat_rollout_steps(
+            self.bank.plan.handle, _ptr(self.bank.data), self.bank.num_problems, _ptr(self.state), _ptr(self.state),
+            _ptr(actions), K, _ptr(self.keys.chain), _ptr(self.keys.next_chain), self.num_envs_global,
+            self.env_offset, _ptr(out.get("obs")), _ptr(out.get("gnn_assignment")),
+            _ptr(out.get("gnn_clause_features")), 1 if out.get("emit_every_step") else 0, _ptr(reward),
+            int(reward.shape[-1]), _ptr(done), int(done.shape[-1]), _ptr(out["solved"]),
+            _ptr(out["num_unsatisfied"]), _ptr(out["episode_step"]), _ptr(out.get("newly_satisfied")),
+            self.num_envs, _stream_ptr(self.state.device)), "msat_rollout_steps")
+        self.keys.flip()
+        return out
+
+    def set_episode_steps(self, steps: torch.Tensor) -> None:
+        """Overwrite the per-env ``state.step`` counters (int32 ``[B]``).  Used to de-phase a freshly reset
+        batch so that episodes time out at different rollout steps (steady-state auto-reset rate
+        ~ B / max_steps per step) instead of all at once."""
+        aw = (self.env.num_vars + 31) // 32
+        self.state[:, aw].copy_(steps.to(device=self.state.device, dtype=torch.int32))
+
+    # ------------------------------------------------------------------ host-buffer stepping
     def alloc_host_io(self) -> Dict[str, torch.Tensor]:
         """Pinned host buffers for ``step_host``: the action batch in, reward/done/info out (same column
         counts as the device outputs)."""
@@ -254,6 +304,60 @@ class VecSATEnv:
             _lib.check(rc, "msat_rollout_step_host")
         self.keys._cur = 1 - cur
         return host
+
+    def alloc_async_io(self, depth: int = 2):
+        """Slots of the double-buffered host pipeline: per slot pinned host buffers (actions in, results out),
+        a device action staging buffer and device result buffers.  Returns a list of slot dicts."""
+        if getattr(self, "_pipe", None) is None:
+            h = C.c_void_p()
+            _lib.check(self.env._lib.msat_host_pipe_create(C.byref(h), int(depth)), "msat_host_pipe_create")
+            self._pipe = h
+            self._pipe_depth = int(depth)
+        slots = []
+        compact = self.out["reward"].shape[-1] == 1
+        for _ in range(self._pipe_depth):
+            host = self.alloc_host_io()
+            dev_out = self.env.alloc_step_outputs(self.num_envs, self.bank.plan.dims, want_obs=False, compact=compact)
+            dev_out["obs"] = self.out["obs"]
+            slots.append({"host": host, "dev": dev_out,
+                          "actions_dev": torch.empty(host["actions"].shape, dtype=torch.int32, device=self.state.device)})
+        return slots
+
+    def step_host_async(self, slot_idx: int, slot: Dict, actions_host: Optional[torch.Tensor] = None) -> None:
+        """Enqueue one rollout step for host buffers without blocking (``msat_rollout_step_host_async``): the
+        action upload, the fused step and the result download of this call overlap the neighbouring steps'.
+        ``actions_host`` (pinned; default ``slot['host']['actions']``) must stay untouched until the step's
+        kernel has run; read the results from ``slot['host']`` after ``host_wait(slot_idx)``."""
+        host, out, dev = slot["host"], slot["dev"], self.state.device
+        acts = host["actions"] if actions_host is None else actions_host
+        k, cur = self.keys, self.keys._cur
+        done, reward = out["done"], out["reward"]
+        rc = self.env._lib.msat_rollout_step_host_async(
+            self._pipe, slot_idx, self.bank.plan.handle, _ptr(self.bank.data), self.bank.num_problems,
+            _ptr(self.state), acts.data_ptr(), slot["actions_dev"].data_ptr(), _ptr(k._bufs[cur]),
+            _ptr(k._bufs[1 - cur]), self.num_envs_global, self.env_offset, _ptr(out["obs"]), _ptr(reward),
+            int(reward.shape[-1]), _ptr(done), int(done.shape[-1]), _ptr(out["solved"]),
+            _ptr(out["num_unsatisfied"]), _ptr(out["episode_step"]), _ptr(host["reward"]), _ptr(host["done"]),
+            _ptr(host["solved"]), _ptr(host["num_unsatisfied"]), _ptr(host["episode_step"]), self.num_envs,
+            torch.cuda.current_stream(dev).cuda_stream)
+        if rc != 0:
+            _lib.check(rc, "msat_rollout_step_host_async")
+        self.keys._cur = 1 - cur
+
+    def host_wait(self, slot_idx: int) -> None:
+        """Block until the results of the step last enqueued on this slot are in its host buffers."""
+        _lib.check(self.env._lib.msat_host_wait(self._pipe, int(slot_idx)), "msat_host_wait")
+
+    def close(self) -> None:
+        if getattr(self, "_pipe", None) is not None:
+            self.env._lib.msat_host_pipe_destroy(self._pipe)
+            self._pipe = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
     def host_views(self, host: Dict[str, torch.Tensor]):
         """Reference-shaped dicts over the host buffers: rewards / dones keyed by agent (+ "__all__"),

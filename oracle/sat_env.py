@@ -72,7 +72,9 @@ class SATEnvOracle:
     """Batched NumPy mirror of ``SATEnv`` (env:28-411)."""
 
     def __init__(self, num_vars, num_clauses, max_steps: int, vars_per_agent: Optional[int] = None,
-                 action_mode: int = 0, r_clause: float = 0.02, r_sat: float = 1.0, gamma: float = 0.99):
+                 action_mode: int = 0, r_clause: float = 0.02, r_sat: float = 1.0, gamma: float = 0.99,
+                 reward_mode: str = "sparse"):
+        self.reward_mode = reward_mode                                  # "shaped": the commented variant env:201-223
         self.num_vars = num_vars
         self.num_clauses = num_clauses
         self.agent_groups = create_agent_groups(num_vars, vars_per_agent)
@@ -180,10 +182,24 @@ class SATEnvOracle:
                       num_unsatisfied=num_unsat, step=(state.step + 1).astype(np.int32),
                       done=np.repeat(done[:, None], A, axis=1))
         r = np.where(solved, np.float32(1.0), np.float32(0.0)).astype(np.float32)    # env:193
+        newly = None
+        if self.reward_mode == "shaped":
+            # env:201-223 (commented out in the reference): PBRS + newly satisfied clauses + terminal bonus,
+            # float32 with one rounding per operation (weak-typed Python floats become f32 in JAX)
+            f32 = np.float32
+            pot_old = (-state.num_unsatisfied).astype(f32)
+            pot_new = (-num_unsat).astype(f32)
+            r_pbrs = f32(self.gamma) * pot_new - pot_old                                 # env:208-210
+            newly = (status & ~state.clauses_satisfied_status).astype(f32).sum(axis=1, dtype=f32)   # env:213
+            r_clause_total = newly * f32(self.r_clause)                                  # env:214
+            r_sat = np.where(solved, f32(self.r_sat), f32(0.0))                          # env:217
+            r = ((r_pbrs + r_clause_total) + r_sat).astype(f32)                          # env:220
         rewards = {a: r for a in self.agents}
         obs = self.get_obs(nxt)
         infos = {"solved": solved, "num_unsatisfied": num_unsat,
                  "episode_step": (state.step + 1).astype(np.int32)}     # env:278-282
+        if newly is not None:
+            infos["newly_satisfied"] = newly.astype(np.int32)
         return obs, nxt, rewards, dones, infos
 
     # -- env:345-398 --------------------------------------------------------

@@ -91,6 +91,24 @@ _metric_nodes = _stmts_between("team_rewards", "avg_steps_to_solve")     # learn
 assert [_assigned_name(s) for s in _norm_nodes] == ["adv_mean", "adv_std", "advantages"]
 
 
+# ------------------------------------------------------------------ the commented-out shaped reward (env:201-223)
+def shaped_reward_env_class():
+    """``SATEnv`` with the alternative ``_calculate_rewards`` that the reference keeps commented out
+    (env:201-223): the comment markers of exactly those lines are stripped and the text is compiled as is."""
+    lines = (REF / "src/envs/multi_agent_sat_env.py").read_text(encoding="utf-8").splitlines()
+    i0 = next(i for i, l in enumerate(lines) if l.startswith("    # def _calculate_rewards"))
+    i1 = next(i for i in range(i0, len(lines)) if lines[i].strip() == "#     return rewards")
+    body = []
+    for l in lines[i0:i1 + 1]:
+        t = l[4:]                                    # drop the method indentation
+        assert t.startswith("#"), l
+        body.append(t[2:] if t.startswith("# ") else t[1:])
+    src = "\n".join(body)
+    ns = {"jnp": jnp, "Dict": dict, "SATState": object}
+    exec(compile(src, "multi_agent_sat_env.py:201-223 (uncommented)", "exec"), ns)
+    return type("SATEnvShaped", (SATEnv,), {"_calculate_rewards": ns["_calculate_rewards"]})
+
+
 # ------------------------------------------------------------------ policy stub (outside the hot path)
 class _StubPi:
     """Stands in for the distrax distribution: ``sample`` plays the pre-drawn action table."""
@@ -155,10 +173,14 @@ def random_ksat(rng, P, n, m, k, kmin=None):
 
 # ------------------------------------------------------------------ one rollout case
 def run_rollout_case(name, n, m, k, P, B, T, max_steps, vpa=None, action_mode=0, seed=0, kmin=None,
-                     wild_actions=False, gamma=0.995, gae_lambda=0.95, dense_graph=False):
+                     wild_actions=False, gamma=0.995, gae_lambda=0.95, dense_graph=False, shaped=None):
     rng = np.random.default_rng(seed)
     with contextlib.redirect_stdout(io.StringIO()) as printed:
-        env = SATEnv(n, m, max_steps, vars_per_agent=vpa, action_mode=action_mode)
+        if shaped is None:
+            env = SATEnv(n, m, max_steps, vars_per_agent=vpa, action_mode=action_mode)
+        else:       # (r_clause, r_sat, gamma) of the commented-out shaped reward
+            env = shaped_reward_env_class()(n, m, max_steps, vars_per_agent=vpa, action_mode=action_mode,
+                                            r_clause=shaped[0], r_sat=shaped[1], gamma=shaped[2])
     wrapper = learner.SATDataWrapper(env)
     A, V = env.num_agents, env.max_vars_per_agent
     clauses = random_ksat(rng, P, n, m, k, kmin)
@@ -205,6 +227,7 @@ def run_rollout_case(name, n, m, k, P, B, T, max_steps, vpa=None, action_mode=0,
     out = {
         "meta": np.array([n, m, k, P, B, T, max_steps, -1 if vpa is None else vpa, action_mode, A, V], np.int64),
         "gamma_lambda": np.array([gamma, gae_lambda], np.float64),
+        "shaped": np.array([0.0, 0.0, 0.0, 0.0] if shaped is None else [1.0, *shaped], np.float64),
         "printed": np.array(printed.getvalue()),
         "agent_vars": np.asarray(env.agent_vars), "action_mask": np.asarray(env.action_mask),
         "variable_to_agent_idx": np.asarray(env.variable_to_agent_idx),
@@ -258,7 +281,7 @@ def run_rollout_case(name, n, m, k, P, B, T, max_steps, vpa=None, action_mode=0,
         out["graph0_A_pos"] = np.asarray(sg.A_pos)
         out["graph0_A_neg"] = np.asarray(sg.A_neg)
     for k_, v in out.items():
-        if isinstance(v, np.ndarray) and v.dtype in (np.float64,) and k_ not in ("gamma_lambda",):
+        if isinstance(v, np.ndarray) and v.dtype in (np.float64,) and k_ not in ("gamma_lambda", "shaped"):
             raise AssertionError(f"{k_}: the shim produced float64")
     np.savez_compressed(HERE / f"env_{name}.npz", **out)
     nres = int(np.asarray(traj.global_done).sum())
@@ -375,6 +398,9 @@ def main():
     run_rollout_case("pad_quirk_n7", 7, 12, 3, P=4, B=5, T=16, max_steps=4, vpa=4, kmin=2, seed=12, dense_graph=True)
     run_rollout_case("single_agent", 9, 20, 3, P=3, B=4, T=12, max_steps=5, vpa=9, seed=13)
     run_rollout_case("one_var_agents", 6, 14, 3, P=3, B=4, T=12, max_steps=5, vpa=1, seed=14)
+    run_rollout_case("shaped_loose12", 12, 20, 3, P=5, B=8, T=40, max_steps=9, seed=15, shaped=(0.02, 1.0, 0.99))
+    run_rollout_case("shaped_uf50_mode1", 50, 218, 3, P=3, B=4, T=10, max_steps=4, action_mode=1, seed=16,
+                     shaped=(0.05, 20.0, 0.995))
     run_stepping_case("past_done_mode0", 12, 20, 3, B=6, T=14, max_steps=4, seed=21)
     run_stepping_case("past_done_mode1", 23, 70, 5, B=5, T=10, max_steps=3, action_mode=1, kmin=2, seed=22)
     run_eval_and_bc_case("eval_bc_loose", 12, 24, 3, num_problems=8, max_steps=25, seed=31)

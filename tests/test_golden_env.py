@@ -20,7 +20,7 @@ from oracle.sat_env import SATEnvOracle
 GOLD = Path(__file__).resolve().parent / "golden"
 ROLLOUT_CASES = ["c1_uf20_mode0", "c1_uf20_mode1", "loose12_mode0", "loose12_mode1", "yaml_uf35_vpa7", "c2_uf50",
                  "c3_uf100", "c4_uf250", "c5_mixedk_vpa7", "c5_mixedk_mode1", "wild_actions_uneven", "pad_quirk_n7",
-                 "single_agent", "one_var_agents"]
+                 "single_agent", "one_var_agents", "shaped_loose12", "shaped_uf50_mode1"]
 STEPPING_CASES = ["past_done_mode0", "past_done_mode1"]
 EVAL_CASES = ["eval_bc_loose", "eval_bc_uneven"]
 GAE_RTOL = 1e-5
@@ -30,6 +30,10 @@ def load(name):
     fx = dict(np.load(GOLD / f"env_{name}.npz"))
     n, m, k, P, B, T, max_steps, vpa, mode, A, V = (int(x) for x in fx["meta"])
     fx["cfg"] = dict(n=n, m=m, k=k, P=P, B=B, T=T, max_steps=max_steps, vpa=None if vpa < 0 else vpa, mode=mode, A=A, V=V)
+    sh = fx.get("shaped")
+    # the reference's commented-out shaped reward (env:201-223), run uncommented by the fixture generator
+    fx["reward_kw"] = ({} if sh is None or sh[0] == 0 else
+                       dict(r_clause=float(sh[1]), r_sat=float(sh[2]), gamma=float(sh[3]), reward_mode="shaped"))
     return fx
 
 
@@ -51,6 +55,7 @@ def test_fixtures_are_reference_outputs():
     """Sanity of the fixtures themselves: every BASELINE config shape is present, episodes end and
     restart inside the rollouts, some are solved, and the F6 padding quirk is exercised."""
     total_resets = total_solved = 0
+    assert np.unique(load("shaped_loose12")["tr_reward"]).size > 6      # the shaped reward is not 0/1
     for name in ROLLOUT_CASES:
         fx = load(name)
         assert fx["tr_local_obs"].dtype == np.int32 and fx["tr_reward"].dtype == np.float32
@@ -77,7 +82,7 @@ def test_fixtures_are_reference_outputs():
 def test_oracle_rollout_matches_reference(name):
     fx = load(name)
     c = fx["cfg"]
-    env = SATEnvOracle(c["n"], c["m"], c["max_steps"], vars_per_agent=c["vpa"], action_mode=c["mode"])
+    env = SATEnvOracle(c["n"], c["m"], c["max_steps"], vars_per_agent=c["vpa"], action_mode=c["mode"], **fx["reward_kw"])
     eq(env.agent_vars, fx["agent_vars"], "agent_vars")
     eq(env.action_mask, fx["action_mask"], "action_mask")
     eq(env.variable_to_agent_idx, fx["variable_to_agent_idx"], "variable_to_agent_idx")
@@ -179,6 +184,8 @@ def test_c_port_rollout_matches_reference(name):
     from oracle.c_port import SATEnvOracleC
     fx = load(name)
     c = fx["cfg"]
+    if fx["reward_kw"]:
+        pytest.skip("the C port implements the active (sparse) reward only")
     cen = SATEnvOracleC(c["n"], c["m"], c["max_steps"], vars_per_agent=c["vpa"], action_mode=c["mode"])
     st = cen.reset(fx["clauses"][fx["initial_indices"]], fx["initial_reset_keys"])
     eq(st["obs"], fx["obs0"], "obs0")
@@ -220,7 +227,8 @@ def test_cuda_rollout_matches_reference(name, fused_keys):
     fx = load(name)
     c = fx["cfg"]
     T, B = c["T"], c["B"]
-    env = M.SATEnv(c["n"], c["m"], c["max_steps"], vars_per_agent=c["vpa"], action_mode=c["mode"], verbose=False)
+    env = M.SATEnv(c["n"], c["m"], c["max_steps"], vars_per_agent=c["vpa"], action_mode=c["mode"], verbose=False,
+                   **fx["reward_kw"])
     eq(_to_np(env.agent_vars), fx["agent_vars"], "agent_vars")
     eq(_to_np(env.action_mask), fx["action_mask"], "action_mask")
     eq(_to_np(env.variable_to_agent_idx), fx["variable_to_agent_idx"], "variable_to_agent_idx")

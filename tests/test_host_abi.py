@@ -75,7 +75,25 @@ def test_argument_errors_enqueue_nothing():
     plan = env._plan_for(3).handle
     assert lib.msat_reset(plan, None, 1, None, None, None, None, 4, None) == _lib.MSAT_EINVAL
     assert lib.msat_step(plan, None, 1, None, None, None, 0, None, None, None, None, 0, None, 0, None, None, None,
-                         4, None) == _lib.MSAT_EINVAL
+                         None, 4, None) == _lib.MSAT_EINVAL
+    # K outside 1..64, missing rng, both kinds of policy input at once
+    dummy = C.addressof((C.c_char * 256)())
+    a16 = (dummy + 127) // 128 * 128
+    base = [plan, a16, 1, a16, a16, a16]
+    tail = [None, 0, None, 0, None, None, None, None, 4, None]
+    assert lib.msat_rollout_steps(*base, 0, a16, a16 + 64, 4, 0, None, None, None, 0, *tail) == _lib.MSAT_EINVAL
+    assert lib.msat_rollout_steps(*base, 65, a16, a16 + 64, 4, 0, None, None, None, 0, *tail) == _lib.MSAT_EINVAL
+    assert lib.msat_rollout_steps(*base, 2, None, a16 + 64, 4, 0, None, None, None, 0, *tail) == _lib.MSAT_EINVAL
+    assert lib.msat_rollout_steps(*base, 2, a16, a16 + 64, 4, 0, a16, a16, None, 0, *tail) == _lib.MSAT_EINVAL
+    # newly_satisfied needs the shaped reward; reward mode must be a known constant
+    assert lib.msat_rollout_steps(*base, 2, a16, a16 + 64, 4, 0, None, None, None, 0, None, 0, None, 0, None, None,
+                                  None, a16, 4, None) == _lib.MSAT_EINVAL
+    assert lib.msat_plan_set_reward(plan, 7, 0.99, 0.02, 1.0) == _lib.MSAT_EINVAL
+    assert lib.msat_tune(b"no_such_knob", 1) == _lib.MSAT_EINVAL
+    h = C.c_void_p()
+    assert lib.msat_host_pipe_create(C.byref(h), 0) == _lib.MSAT_EINVAL
+    assert lib.msat_host_pipe_create(C.byref(h), 9) == _lib.MSAT_EINVAL
+    assert lib.msat_host_wait(None, 0) == _lib.MSAT_EINVAL
     assert lib.msat_env_keys(None, None, 8, 4, 8, 3, None, None, None) == _lib.MSAT_EINVAL   # shard exceeds batch
     assert lib.msat_gae(None, 1, 1, None, None, None, 0.9, 0.9, None, None, None, 4, 4, None) == _lib.MSAT_EINVAL
     buf = (C.c_char * 4096)()
