@@ -95,7 +95,7 @@ def _cpu_worker(args):
     return time.perf_counter() - t0
 
 
-def run_cpu_restatement_c(wname, envs_per_core, steps, warmup):
+def run_cpu_restatement_c(wname, envs_per_core, steps, warmup, total_envs=None):
     """Compiled CPU baseline: the plain-C + OpenMP restatement (oracle/sat_env_c.c), all host cores."""
     import numpy as np
     from oracle import rollout as orollout
@@ -106,7 +106,7 @@ def run_cpu_restatement_c(wname, envs_per_core, steps, warmup):
     env = SATEnvOracleC(w["n"], w["m"], MAX_STEPS, vars_per_agent=w["vpa"])
     env.set_threads(cores)              # torchrun exports OMP_NUM_THREADS=1 to every rank
     threads = env.num_threads()
-    envs = envs_per_core * max(cores, 1)
+    envs = total_envs or envs_per_core * max(cores, 1)
     problems = make_formulas(w, envs, 1000)
     key, idx, rk = orollout.initial_reset_inputs(otf.prng_key(SEED), envs, envs)
     st = env.reset(problems[idx], rk)
@@ -279,6 +279,17 @@ class ClockSampler:
 # ----------------------------------------------------------------------------------------------
 # CUDA arm
 # ----------------------------------------------------------------------------------------------
+def _time_steps(torch, fn, count):
+    """CUDA-event time (ms) of `count` calls of fn(i) on the current stream."""
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(count):
+        fn(i)
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1)
+
+
 def main_ours(args):
     import torch
     import torch.distributed as dist
@@ -320,7 +331,17 @@ def main_ours(args):
     A, V = env.num_agents, env.max_vars_per_agent
     gen = torch.Generator(device=dev).manual_seed(1234 + shard_rank)
     actions = torch.randint(0, V + 1, (ACTION_CYCLE, B, A), generator=gen, device=dev, dtype=torch.int32)
+
+    def dephase(v):
+        """Fresh batch -> steady state: env g starts at episode step g mod max_steps, so ~B/max_steps envs time
+        out (and auto-reset inside the step kernel) at EVERY rollout step instead of all of them at step 512."""
+        g = torch.arange(v.env_offset, v.env_offset + v.num_envs, device=dev, dtype=torch.int64)
+        v.set_episode_steps((g % v.env.max_steps).to(torch.int32))
+
     vec.reset()
+    dephase(vec)
+    reset_counter = torch.zeros(1, dtype=torch.int64, device=dev)
+    env.count_resets(w["k"], reset_counter)
     torch.cuda.synchronize()
 
     def barrier():
@@ -335,7 +356,9 @@ def main_ours(args):
                         compact_outputs=True)
     vec_h.out["obs"] = vec.out["obs"]
     vec_h.reset()
+    dephase(vec_h)
     host = vec_h.alloc_host_io()
+    slots = vec_h.alloc_async_io(depth=2)
     host_actions = [actions[i].cpu().pin_memory() for i in range(4)]
     torch.cuda.synchronize()
     sampler = ClockSampler(local_rank) if rank == 0 else None
@@ -347,10 +370,13 @@ def main_ours(args):
         vec.step(actions[i % ACTION_CYCLE])
     torch.cuda.synchronize()
     graph = None
-    if args.graph > 0:
+    graph_steps = args.graph
+    if graph_steps < 0:     # auto: at <= 16,384 envs per GPU the ~85-170 us step is short enough for the launch gap to show
+        graph_steps = 32 if B <= 16384 else 0
+    if graph_steps > 0:
         # launch-bound regime (small per-GPU batches): capture a block of G rollout steps (G even, so the
         # ping-pong rng buffers end where they started) and replay it; the remainder is launched directly
-        G = max(2, args.graph - args.graph % 2)
+        G = max(2, graph_steps - graph_steps % 2)
         graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(graph):
             for i in range(G):
@@ -369,6 +395,7 @@ def main_ours(args):
             vec.step(actions[i % ACTION_CYCLE])
 
     barrier()
+    reset_counter.zero_()
     torch.cuda.synchronize()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t_wall0 = time.perf_counter()
@@ -381,40 +408,86 @@ def main_ours(args):
         sampler.stop()
     barrier()
     ms = ev0.elapsed_time(ev1)
+    resets_timed = int(reset_counter.item())
     launches = K                           # one fused msat_rollout_step launch per step
 
-    # ---- dominant kernel alone (roofline): K launches of msat_step, same arguments --------------
-    kev0, kev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    # ---- dominant kernel alone (roofline): K launches of the same fused step, back to back ---------------
     for i in range(3):
-        env.step_into(bank, vec.state, vec.state, actions[i], vec.out, auto_reset=True,
-                      new_problem_idx=vec.new_problem_idx, reset_keys=vec.reset_keys)
+        vec.step(actions[i])
     torch.cuda.synchronize()
-    kev0.record()
-    for i in range(K):
-        env.step_into(bank, vec.state, vec.state, actions[i % ACTION_CYCLE], vec.out, auto_reset=True,
-                      new_problem_idx=vec.new_problem_idx, reset_keys=vec.reset_keys)
-    kev1.record()
-    torch.cuda.synchronize()
-    kernel_ms = kev0.elapsed_time(kev1) / K
+    kernel_ms = _time_steps(torch, lambda i: vec.step(actions[i % ACTION_CYCLE]), K) / K
 
-    # ---- end to end through the host-buffer entry point: `e2e` -------------------------------------
-    Ke = max(1, min(K, args.e2e_steps))
-    for i in range(2):
-        host["actions"].copy_(host_actions[i % 4])
-        vec_h.step_host(host)
+    # ---- auto-reset cost: the same step with 25 % and 100 % of the envs resetting every step -----------------
+    reset_legs = {}
+    if not args.no_reset_legs:
+        for label, max_steps in (("reset_heavy", 4), ("all_reset", 1)):
+            env_r = M.SATEnv(w["n"], w["m"], max_steps, vars_per_agent=w["vpa"], verbose=False, device=dev,
+                             group_threads=args.group_threads)
+            vec_r = M.VecSATEnv(env_r, bank.for_env(env_r), Bg, M.prng_key(SEED + 3), world_size=shard_world,
+                                rank=shard_rank, emit_obs=False)
+            vec_r.out["obs"] = vec.out["obs"]
+            cnt = torch.zeros(1, dtype=torch.int64, device=dev)
+            env_r.count_resets(w["k"], cnt)
+            vec_r.reset()
+            dephase(vec_r)
+            for i in range(4):
+                vec_r.step(actions[i])
+            cnt.zero_()
+            Kr = min(K, 40)
+            r_ms = _time_steps(torch, lambda i: vec_r.step(actions[i % ACTION_CYCLE]), Kr) / Kr
+            reset_legs[label] = {"max_steps": max_steps, "ms_per_step": r_ms, "steps": Kr,
+                                 "autoreset_frac": int(cnt.item()) / float(B * Kr),
+                                 "value": Bg / (r_ms * 1e-3)}
+            env_r.count_resets(w["k"], None)
+            del vec_r, env_r
+
+    # ---- end to end through the host-buffer entry points: `e2e` ------------------------------------------------
+    # Double-buffered pipeline (msat_rollout_step_host_async): per step the host hands over a pinned action
+    # batch, the library uploads it, runs the fused step and downloads reward / done / info into pinned
+    # memory; the host reads the results of step t-2 while steps t-1 and t are in flight.
+    Ke = max(4, min(K, args.e2e_steps))
+    sink = [0]
+
+    def harvest(slot):
+        vec_h.host_wait(slot)
+        h = slots[slot]["host"]
+        sink[0] += int(h["solved"][0]) + int(h["done"][0, 0])     # the host reads the step's result
+
+    def e2e_async(n):
+        for t in range(n):
+            sl = t & 1
+            if t >= 2:
+                harvest(sl)
+            vec_h.step_host_async(sl, slots[sl], actions_host=host_actions[t % 4])
+        harvest(n & 1)
+        harvest((n + 1) & 1)
+    e2e_async(4)
     torch.cuda.synchronize()
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    tw0 = time.perf_counter()
     e0.record()
-    for i in range(Ke):
+    e2e_async(Ke)
+    e1.record()
+    torch.cuda.synchronize()
+    e2e_wall_ms = 1e3 * (time.perf_counter() - tw0)
+    barrier()
+    e2e_ms = max(e0.elapsed_time(e1), 0.0)
+    # the synchronous single-call variant (msat_rollout_step_host: upload, step, download, stream sync per call)
+    for i in range(2):
+        host["actions"] = host_actions[i % 4]
+        vec_h.step_host(host)
+    torch.cuda.synchronize()
+    barrier()
+
+    def sync_step(i):
         host["actions"] = host_actions[i % 4]
         vec_h.step_host(host)
         rewards, dones, infos = vec_h.host_views(host)      # reference-shaped dicts (views)
-        _ = int(infos["solved"][0]) + int(dones["__all__"][0])   # the host reads the step's result
-    e1.record()
-    torch.cuda.synchronize()
+        sink[0] += int(infos["solved"][0]) + int(dones["__all__"][0])
+    Ks = min(Ke, 30)
+    e2e_sync_ms = _time_steps(torch, sync_step, Ks)
     barrier()
-    e2e_ms = e0.elapsed_time(e1)
     h2d = B * A * 4
     d2h = B * (4 + 1 + 1 + 4 + 4)           # team reward, done, solved, num_unsatisfied, episode_step
 
@@ -437,11 +510,41 @@ def main_ours(args):
         e2e_obs = (o0.elapsed_time(o1), obs_host.numel() * 4)
         del obs_host
 
+    # ---- K fused steps per launch (msat_rollout_steps): launch-bound small batches -----------------------------
+    kstep_info = None
+    if not args.no_kstep_leg and B <= 16384:
+        Kf = 32
+        outs = vec.alloc_multi_step_outputs(Kf, emit_every_step=False)
+        outs["obs"] = vec.out["obs"]
+        tbl = actions[:Kf].contiguous()
+        for _ in range(2):
+            vec.steps(tbl, outs)
+        reps = max(1, min(K, 320) // Kf)
+        f_ms = _time_steps(torch, lambda i: vec.steps(tbl, outs), reps) / (reps * Kf)
+        del outs
+        obs_all = None
+        try:
+            outs_all = vec.alloc_multi_step_outputs(Kf, emit_every_step=True)
+            for _ in range(2):
+                vec.steps(tbl, outs_all)
+            fa_ms = _time_steps(torch, lambda i: vec.steps(tbl, outs_all), reps) / (reps * Kf)
+            del outs_all
+        except torch.OutOfMemoryError:
+            fa_ms = None
+        kstep_info = {"steps_per_launch": Kf, "launches": reps,
+                      "final_obs_only": {"ms_per_step": f_ms, "value": Bg / (f_ms * 1e-3),
+                                         "what": "K steps per launch, observations of the final state only"},
+                      "obs_every_step": None if fa_ms is None else {
+                          "ms_per_step": fa_ms, "value": Bg / (fa_ms * 1e-3),
+                          "what": "K steps per launch, int32 observations written for every step into [K,B,A,D]"},
+                      "what": "msat_rollout_steps: one launch for 32 rollout steps of an action table; state and "
+                              "formula stay in shared memory across the steps"}
+
     # ---- MAPPO advantage path on the same batch (learner:504-532): T x B GAE scan + normalisation -------
     gae_info = None
-    if world == 1 and not args.no_gae:
+    if not args.no_gae:
         T = args.gae_steps
-        gg = torch.Generator(device=dev).manual_seed(7)
+        gg = torch.Generator(device=dev).manual_seed(7 + shard_rank)
         g_reward = (torch.rand((T, B), generator=gg, device=dev) < 0.01).float()
         g_done = (torch.rand((T, B), generator=gg, device=dev) < 0.005).to(torch.uint8)
         g_value = torch.randn((T, B), generator=gg, device=dev)
@@ -458,8 +561,9 @@ def main_ours(args):
             stats.zero_()
             adv, tgt = M.calculate_gae(g_reward, g_done, g_value, g_last, 0.995, 0.95, stats=stats)
         g1.record()
+        raw = adv.clone()
         for _ in range(reps):
-            M.normalize_advantages(adv, stats=stats)
+            M.normalize_advantages(adv, stats=stats)         # all-reduces the 24-byte statistics when world > 1
         g2.record()
         torch.cuda.synchronize()
         scan_ms, norm_ms = g0.elapsed_time(g1) / reps, g1.elapsed_time(g2) / reps
@@ -468,7 +572,24 @@ def main_ours(args):
                     "normalize_bytes_per_element": 8, "normalize_gbs": 8.0 * T * B / (norm_ms * 1e-3) / 1e9,
                     "note": "synthetic rollout, inputs resident in HBM; 17 B/element = reward 4 + done 1 + value 4 + "
                             "adv 4 + target 4, advantage statistics accumulated in the same pass; normalisation = "
-                            "one in-place map (8 B)"}
+                            "one in-place map (8 B)" + ("; with world > 1 normalize_ms includes the NCCL all-reduce "
+                                                        "of (count, sum, sum of squares)" if world > 1 else "")}
+        if world > 1:
+            # self-check of the sharded normalisation: gather every rank's raw advantages on rank 0 and compare
+            # the sharded result with the full-batch computation
+            M.normalize_advantages(raw, stats=stats)
+            parts = [torch.empty_like(g_value) for _ in range(world)] if rank == 0 else None
+            raws = [torch.empty_like(g_value) for _ in range(world)] if rank == 0 else None
+            adv2, _ = M.calculate_gae(g_reward, g_done, g_value, g_last, 0.995, 0.95)
+            dist.gather(raw, parts, dst=0)
+            dist.gather(adv2, raws, dst=0)
+            if rank == 0:
+                full = torch.cat(raws, dim=1).double()
+                ref = (full - full.mean()) / (full.var(unbiased=False).sqrt() + 1e-8)
+                err = (torch.cat(parts, dim=1).double() - ref).abs().max().item()
+                gae_info["sharded_vs_full_batch_max_abs_err"] = err
+                if err > 1e-4:
+                    raise SystemExit(f"sharded advantage normalisation differs from the full batch: {err}")
         del g_reward, g_done, g_value, g_last, adv, tgt
 
     # ---- extra: the reference policy's actual input ----------------------
@@ -481,30 +602,40 @@ def main_ours(args):
         vec_g = M.VecSATEnv(env, bank, Bg, M.prng_key(SEED + 2), emit_obs=False, compact_outputs=True,
                             gnn_outputs=True)
         vec_g.reset()
+        dephase(vec_g)
         static_graph(bank)                      # per-formula part, once
         for i in range(5):
             vec_g.step(actions[i])
         torch.cuda.synchronize()
-        q0, q1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         Kg = min(K, 100)
-        q0.record()
-        for i in range(Kg):
-            vec_g.step(actions[i % ACTION_CYCLE])
-        q1.record()
-        torch.cuda.synchronize()
-        g_ms = q0.elapsed_time(q1) / Kg
+        g_ms = _time_steps(torch, lambda i: vec_g.step(actions[i % ACTION_CYCLE]), Kg) / Kg
+        d = bank.plan.dims
+        lits_bytes = (w["m"] * w["k"] * 2 + 15) // 16 * 16
+        g_bytes = (4 * w["n"] + 12 * w["m"] + lits_bytes + 2 * 4 * d.state_words + 4 * A + 4 + 1 + 1 + 4 + 4)
         gnn_info = {"value": Bg / (g_ms * 1e-3), "unit": UNIT, "ms_per_step": g_ms, "steps": Kg,
                     "bytes_out_per_env_step": 4 * w["n"] + 12 * w["m"],
+                    "bytes_moved_per_env_step": g_bytes,
+                    "gbs": g_bytes * B / (g_ms * 1e-3) / 1e9,
                     "what": "msat_rollout_step_gnn: one launch per step, no local observations, dynamic GNN input "
-                            "(assignment int32[B,n], clause_features float32[B,m,3]) emitted from the staged formula "
-                            "record; static graph features emitted once per formula bank"}
+                            "(assignment int32[B,n], clause_features float32[B,m,3]) emitted from the staged literal "
+                            "block; static graph features emitted once per formula bank; bytes_moved = outputs + "
+                            "packed literal block + state r/w + actions + reward/done/info"}
         del vec_g
+    env.count_resets(w["k"], None)
 
     # ---- reduce over ranks (max time) ------------------------------------------------------------------
-    t = torch.tensor([ms, kernel_ms, e2e_ms, e2e_obs[0] if e2e_obs else 0.0], dtype=torch.float64, device=dev)
+    t = torch.tensor([ms, kernel_ms, e2e_ms, e2e_obs[0] if e2e_obs else 0.0, e2e_sync_ms, e2e_wall_ms,
+                      reset_legs.get("reset_heavy", {}).get("ms_per_step", 0.0),
+                      reset_legs.get("all_reset", {}).get("ms_per_step", 0.0),
+                      gae_info["scan_ms"] if gae_info else 0.0, gae_info["normalize_ms"] if gae_info else 0.0],
+                     dtype=torch.float64, device=dev)
+    rs = torch.tensor([resets_timed], dtype=torch.int64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms, kernel_ms_max, e2e_ms, e2e_obs_ms = [float(x) for x in t.tolist()]
+        dist.all_reduce(rs, op=dist.ReduceOp.SUM)
+    (ms, kernel_ms_max, e2e_ms, e2e_obs_ms, e2e_sync_ms, e2e_wall_ms, heavy_ms, allr_ms, scan_ms_max,
+     norm_ms_max) = [float(x) for x in t.tolist()]
+    resets_timed = int(rs.item())
 
     if rank == 0:
         alg = algorithmic_bytes_per_env_step(w["n"], w["m"], w["k"], A)
@@ -514,54 +645,95 @@ def main_ours(args):
         else:
             peak, peak_src = 6650.0, "of fallback (B200_PROFILING.md 6.65 TB/s)"
         achieved = alg * B / (kernel_ms * 1e-3) / 1e9          # rank 0's own kernel time
-        traffic = None
+        traffic, traffic_src = None, None
         tf = ROOT / "profiles" / "traffic.json"
         if tf.exists():
             try:
                 rec = json.loads(tf.read_text()).get(f"{wname}:{B}")
-                traffic = rec["dram_bytes_per_launch"] if rec else None
+                if rec:
+                    traffic = rec["dram_bytes_per_launch"]
+                    traffic_src = (f"ncu --set full capture {rec.get('source', 'profiles/')} of this kernel at this "
+                                   f"shape and batch (committed; NOT measured in this run)")
             except Exception:
                 traffic = None
         value = Bg * K / (ms * 1e-3)
+        d = bank.plan.dims
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": ms / K, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
             "dtype": "u32", "data": "synthetic",
             "config": {"workload": f"{wname}: uniform random {w['k']}-SAT n={w['n']} m={w['m']}, {A} agents x {V} vars, "
                                    f"obs_dim {env.obs_dim}, {Bg} envs sharded over {world} GPU(s) ({B} on rank 0), "
-                                   f"{P} distinct formulas, max_steps {MAX_STEPS}, auto-reset on, action_mode 0",
+                                   f"{P} distinct formulas, max_steps {MAX_STEPS}, auto-reset on (episodes de-phased: "
+                                   f"env g starts at step g mod {MAX_STEPS}), action_mode 0",
                        "envs_global": Bg, "envs_per_gpu": B, "problems": P,
-                       "group_threads": bank.plan.dims.group_threads,
+                       "group_threads": d.group_threads,
                        "launch": f"CUDA graph of {G} steps" if graph is not None else "one kernel launch per step",
                        "l2": f"no flush: each step writes {B * A * env.obs_dim * 4 / 1e6:.0f} MB of observations per GPU "
-                             f"(> 126 MB L2) and cycles {ACTION_CYCLE} action batches"},
+                             f"(> 126 MB L2) and cycles {ACTION_CYCLE} action batches"
+                             if B * A * env.obs_dim * 4 > 126e6 else
+                             f"no flush and the per-step working set ({B * A * env.obs_dim * 4 / 1e6:.0f} MB of "
+                             f"observations per GPU) fits the 126 MB L2: writes may be absorbed by L2"},
+            "autoreset_in_timed_region": {"resets": resets_timed, "env_steps": Bg * K,
+                                          "frac": resets_timed / float(Bg * K)},
+            "autoreset_frac_in_timed_region": resets_timed / float(Bg * K),
             "clocks": sampler.summary(t_wall0, t_wall1),
             "e2e": {"value": Bg * Ke / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d * world,
-                    "d2h_bytes_per_step": d2h * world, "steps": Ke,
-                    "what": "VecSATEnv.step_host -> msat_rollout_step_host: pinned host actions in; team reward, done, "
-                            "solved, num_unsatisfied, episode_step out to pinned host memory, expanded to the "
-                            "reference's per-agent dicts as views and read by the host every step; observations "
-                            "stay in HBM for the policy"},
+                    "d2h_bytes_per_step": d2h * world, "steps": Ke, "wall_ms_per_step": e2e_wall_ms / Ke,
+                    "what": "VecSATEnv.step_host_async -> msat_rollout_step_host_async (depth-2 pipeline): every step "
+                            "uploads a pinned host action batch, runs the fused step and downloads team reward, "
+                            "done, solved, num_unsatisfied, episode_step into pinned host memory; the host reads "
+                            "the results of step t-2 while steps t-1 / t are in flight; observations stay in HBM "
+                            "for the policy"},
+            "e2e_sync": {"value": Bg * Ks / (e2e_sync_ms * 1e-3), "unit": UNIT, "steps": Ks,
+                         "what": "msat_rollout_step_host: one blocking call per step (upload, step, download, stream "
+                                 "synchronise), results expanded to the reference's per-agent dicts as views"},
             "gpu_launches": launches,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": traffic, "peak_source": peak_src, "kernel": "msat::env_kernel<GS, MODE_STEP>",
-                         "kernel_ms": kernel_ms, "algorithmic_bytes_per_env_step": alg, "envs_per_launch": B},
+                         "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
+                         "kernel": "msat::env_kernel<GS, MODE_STEP, OBS> (msat_rollout_step)",
+                         "kernel_ms": kernel_ms, "algorithmic_bytes_per_env_step": alg, "envs_per_launch": B,
+                         "achieved_dram_gbs": None if traffic is None else traffic / (kernel_ms * 1e-3) / 1e9,
+                         "note": "achieved = SURVEY 8(d) algorithmic bytes (int32 literals counted at 4 B each) / "
+                                 "kernel time; the kernel reads the formula as packed u16 codes, so its real DRAM "
+                                 "traffic is ~3 % below the algorithmic figure and frac can read slightly above 1 "
+                                 "when the kernel sits at the copy bandwidth"},
         }
+        if reset_legs:
+            reset_legs["reset_heavy"]["ms_per_step"] = heavy_ms
+            reset_legs["all_reset"]["ms_per_step"] = allr_ms
+            for v in reset_legs.values():
+                v["value"] = Bg / (v["ms_per_step"] * 1e-3)
+            line["reset_heavy"] = reset_legs["reset_heavy"]
+            line["all_reset"] = reset_legs["all_reset"]
         if e2e_obs:
             line["e2e_obs_to_host"] = {"value": Bg * args.e2e_obs_steps / (e2e_obs_ms * 1e-3), "unit": UNIT,
                                        "d2h_bytes_per_step": (d2h + e2e_obs[1]) * world, "steps": args.e2e_obs_steps,
-                                       "what": "as e2e, plus the int32 observations copied to pinned host memory"}
+                                       "what": "as e2e_sync, plus the int32 observations copied to pinned host memory"}
+        if kstep_info:
+            line["multi_step_launch"] = kstep_info
         if gnn_info:
+            gnn_info["frac_of_hbm_peak"] = gnn_info["gbs"] / peak
             line["gnn_input_mode"] = gnn_info
         if gae_info:
+            gae_info["scan_ms"], gae_info["normalize_ms"] = scan_ms_max, norm_ms_max
+            gae_info["scan_gbs"] = 17.0 * gae_info["num_steps"] * B / (scan_ms_max * 1e-3) / 1e9
+            gae_info["normalize_gbs"] = 8.0 * gae_info["num_steps"] * B / (norm_ms_max * 1e-3) / 1e9
             gae_info["scan_frac_of_hbm_peak"] = gae_info["scan_gbs"] / peak
+            gae_info["normalize_frac_of_hbm_peak"] = gae_info["normalize_gbs"] / peak
             line["gae"] = gae_info
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"], _ = run_cpu_restatement(wname, args.cpu_envs_per_core, 5, 1)
+            try:        # BASELINE configs[0]: the reference's own CPU-runnable case (uf20-91 x 16 envs)
+                c1, _ = run_cpu_restatement_c("uf20-91", 1, 200, 10, total_envs=16)
+                line["cpu_baseline_c1"] = c1
+            except Exception as e:
+                line["cpu_baseline_c1"] = {"error": repr(e)}
         print(json.dumps(line))
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+    vec_h.close()
     return 0
 
 
@@ -583,8 +755,11 @@ def parse_args(argv=None):
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-gae", action="store_true")
     ap.add_argument("--no-gnn-leg", action="store_true")
-    ap.add_argument("--graph", type=int, default=0, metavar="G",
-                    help="replay the rollout steps as CUDA graphs of G steps each (0 = plain launches)")
+    ap.add_argument("--graph", type=int, default=-1, metavar="G",
+                    help="replay the rollout steps as CUDA graphs of G steps each (0 = plain launches; default -1 = "
+                         "32-step graphs when a GPU owns <= 16,384 envs, plain launches above)")
+    ap.add_argument("--no-reset-legs", action="store_true")
+    ap.add_argument("--no-kstep-leg", action="store_true")
     ap.add_argument("--gae-steps", type=int, default=512, help="T of the GAE leg (configs/MAPPO_CONFIG.yaml NUM_STEPS)")
     ap.add_argument("--emulate-shard", type=int, nargs=2, metavar=("WORLD", "RANK"), default=None,
                     help="debug: single process, but own the env shard of RANK out of WORLD")

@@ -243,6 +243,10 @@ int msat_host_wait(msat_host_pipe* pipe, int32_t slot);
 /* Releases the library's internal per-device streams / events (msat_rollout_step_host). */
 int msat_shutdown(void);
 
+/* Diagnostics: while `counter_dev` (a device uint64, 8-byte aligned, owned by the caller) is set, every
+ * auto-reset performed by a step launch that uses this plan adds 1 to it.  NULL switches it off. */
+int msat_plan_set_reset_counter(msat_plan* plan, uint64_t* counter_dev);
+
 /* Process-wide measurement knobs (A/B comparisons in bench.py; not part of the drop-in surface):
  *   "gae_plain" 1 = msat_gae keeps the register-chunked scan instead of the cp.async-pipelined one. */
 int msat_tune(const char* key, int32_t value);

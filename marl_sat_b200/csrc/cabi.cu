@@ -98,6 +98,7 @@ inline void fill_reward(EnvArgs& a, const msat_plan* plan, int32_t* newly) {
     a.r_clause = plan->r_clause;
     a.r_sat = plan->r_sat;
     a.newly_sat = newly;
+    a.reset_count = plan->reset_counter;
 }
 
 }  // namespace
@@ -179,6 +180,12 @@ int msat_plan_set_reward(msat_plan* plan, int32_t mode, double gamma, double r_c
     plan->r_gamma = (float)gamma;
     plan->r_clause = (float)r_clause;
     plan->r_sat = (float)r_sat;
+    return MSAT_OK;
+}
+
+int msat_plan_set_reset_counter(msat_plan* plan, uint64_t* counter_dev) {
+    if (!plan || (reinterpret_cast<uintptr_t>(counter_dev) & 7)) return MSAT_EINVAL;
+    plan->reset_counter = reinterpret_cast<unsigned long long*>(counter_dev);
     return MSAT_OK;
 }
 

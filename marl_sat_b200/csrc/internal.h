@@ -14,6 +14,7 @@ struct msat_plan {
     int compile_smem_bytes;
     int reward_mode = 0;       // MSAT_REWARD_SPARSE / MSAT_REWARD_SHAPED (msat_plan_set_reward)
     float r_gamma = 0.99f, r_clause = 0.02f, r_sat = 1.0f;
+    unsigned long long* reset_counter = nullptr;   // device counter of auto-resets (diagnostics), or null
     // devices on which the > 48 KB dynamic shared memory opt-in of the env kernels has been made (bit = device
     // ordinal); set once per (plan, device) instead of once per launch
     mutable std::atomic<unsigned long long> prepared_devices{0};
@@ -86,6 +87,7 @@ struct EnvArgs {
     int reward_mode;
     float r_gamma, r_clause, r_sat;
     int32_t* newly_sat;         // optional int32[(K,) B]: clauses satisfied now that were not before the step
+    unsigned long long* reset_count;   // optional device counter: += 1 for every auto-reset (msat_plan_set_reset_counter)
 };
 
 enum EnvMode { MODE_RESET = 0, MODE_STEP = 1, MODE_OBS = 2 };

@@ -512,6 +512,7 @@ __global__ void __launch_bounds__(kCtaThreads, MULTI ? 4 : 8) env_kernel(const D
                 pidx = pidx < 0 ? 0 : (pidx >= a.P ? a.P - 1 : pidx);
                 if (gt == 0) {
                     misc[0] = 0;
+                    if (a.reset_count) atomicAdd(a.reset_count, 1ULL);
                     if (pidx != loaded_pidx) {
                         fence_proxy_async();
                         mbar_expect_tx(bar, tma_bytes);

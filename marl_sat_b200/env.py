@@ -130,6 +130,19 @@ class FormulaBank:
                                               _stream_ptr(device)), "msat_compile_bank")
 
 
+    def for_env(self, env: "SATEnv") -> "FormulaBank":
+        """The same compiled records bound to another env object of the same shape and grouping (e.g. a
+        different ``max_steps`` or reward variant): the record layout depends only on (n, m, k, A)."""
+        d0, plan = self.plan.dims, env._plan_for(self.k)
+        d1 = plan.dims
+        if (d0.n, d0.m, d0.k, d0.A, d0.rec_bytes) != (d1.n, d1.m, d1.k, d1.A, d1.rec_bytes):
+            raise ValueError("for_env needs an env with the same (n, m, k, agents)")
+        other = object.__new__(FormulaBank)
+        other.__dict__.update(self.__dict__)
+        other.env, other.plan = env, plan
+        return other
+
+
 class SATState:
     """Mirror of the reference ``SATState`` (env:13-24) plus the jaxmarl ``State`` fields
     (``done``, ``step``).  Holds the packed per-env device record; the reference-shaped leaves
@@ -260,6 +273,12 @@ class SATEnv:
             self._plans[k] = _Plan(self.num_vars, self.num_clauses, k, self.num_agents, self.action_mode,
                                    self.max_steps, self._group_threads, reward)
         return self._plans[k]
+
+    def count_resets(self, k: int, counter: Optional[torch.Tensor]) -> None:
+        """Diagnostics: route the auto-reset count of every step launch on formulas of width ``k`` into
+        ``counter`` (a zeroed int64[1] device tensor), or switch it off with ``None``."""
+        _lib.check(self._lib.msat_plan_set_reset_counter(self._plan_for(k).handle, _ptr(counter)),
+                   "msat_plan_set_reset_counter")
 
     def make_bank(self, clauses: ArrayLike, validate: bool = True) -> FormulaBank:
         return FormulaBank(self, clauses, validate=validate)
