@@ -370,29 +370,49 @@ def main_ours(args):
         vec.step(actions[i % ACTION_CYCLE])
     torch.cuda.synchronize()
     graph = None
-    graph_steps = args.graph
-    if graph_steps < 0:     # auto: at <= 16,384 envs per GPU the ~85-170 us step is short enough for the launch gap to show
-        graph_steps = 32 if B <= 16384 else 0
-    if graph_steps > 0:
-        # launch-bound regime (small per-GPU batches): capture a block of G rollout steps (G even, so the
-        # ping-pong rng buffers end where they started) and replay it; the remainder is launched directly
-        G = max(2, graph_steps - graph_steps % 2)
+    obs_bytes_per_step = B * A * env.obs_dim * 4
+    mode = args.launch
+    if mode == "auto":
+        # L2-resident batches are launch/latency-bound: K fused steps per launch; up to 16,384 envs per GPU the
+        # ~85-170 us step is short enough for the launch gap to show: CUDA graphs; above that plain launches
+        mode = "multi" if obs_bytes_per_step <= 126e6 else ("graph" if B <= 16384 else "step")
+    if args.graph >= 0:
+        mode = "graph" if args.graph > 0 else ("step" if mode == "graph" else mode)
+    G = 0
+    multi_out = None
+    if mode == "graph":
+        # capture a block of G rollout steps (G even, so the ping-pong rng buffers end where they started) and
+        # replay it; the remainder is launched directly
+        G = max(2, (args.graph if args.graph > 0 else 32) // 2 * 2)
         graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(graph):
             for i in range(G):
                 vec.step(actions[i % ACTION_CYCLE])
         torch.cuda.synchronize()
+    elif mode == "multi":
+        # msat_rollout_steps: 32 steps of the pre-generated action table per launch, the int32 observations of
+        # EVERY step written to a [32, B, A, D] buffer (same bytes per step as the single-step launch)
+        G = 32
+        multi_out = vec.alloc_multi_step_outputs(G, emit_every_step=True)
+        vec.steps(actions[:G], multi_out)
+        torch.cuda.synchronize()
 
     def run_steps(count, first):
-        if graph is None:
+        if mode == "step":
             for i in range(count):
                 vec.step(actions[(first + i) % ACTION_CYCLE])
             return
         reps, rem = divmod(count, G)
-        for _ in range(reps):
-            graph.replay()
-        for i in range(rem):
-            vec.step(actions[i % ACTION_CYCLE])
+        if mode == "graph":
+            for _ in range(reps):
+                graph.replay()
+            for i in range(rem):
+                vec.step(actions[i % ACTION_CYCLE])
+        else:
+            for r in range(reps):
+                vec.steps(actions[(r % 2) * G:(r % 2) * G + G], multi_out)
+            if rem:
+                vec.steps(actions[:rem], multi_out)
 
     barrier()
     reset_counter.zero_()
@@ -409,7 +429,7 @@ def main_ours(args):
     barrier()
     ms = ev0.elapsed_time(ev1)
     resets_timed = int(reset_counter.item())
-    launches = K                           # one fused msat_rollout_step launch per step
+    launches = K if mode != "multi" else (K // G + (1 if K % G else 0))    # fused step launches in the timed region
 
     # ---- dominant kernel alone (roofline): K launches of the same fused step, back to back ---------------
     for i in range(3):
@@ -549,22 +569,47 @@ def main_ours(args):
         g_done = (torch.rand((T, B), generator=gg, device=dev) < 0.005).to(torch.uint8)
         g_value = torch.randn((T, B), generator=gg, device=dev)
         g_last = torch.randn((B,), generator=gg, device=dev)
-        adv = None
+        adv = torch.empty((T, B), dtype=torch.float32, device=dev)
+        tgt = torch.empty((T, B), dtype=torch.float32, device=dev)
+        stats = torch.zeros(3, dtype=torch.float64, device=dev)
+        reps = 10
+
+        def scan_once():
+            stats.zero_()
+            M.calculate_gae(g_reward, g_done, g_value, g_last, 0.995, 0.95, stats=stats, out=(adv, tgt))
+
+        def norm_once():
+            M.normalize_advantages(adv, stats=stats)         # all-reduces the 24-byte statistics when world > 1
         for _ in range(3):
-            adv, tgt = M.calculate_gae(g_reward, g_done, g_value, g_last, 0.995, 0.95)
+            scan_once()
+        raw = adv.clone()
+        norm_once()
         torch.cuda.synchronize()
         g0, g1, g2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
-        reps = 10
-        stats = torch.zeros(3, dtype=torch.float64, device=dev)
-        g0.record()
-        for _ in range(reps):
-            stats.zero_()
-            adv, tgt = M.calculate_gae(g_reward, g_done, g_value, g_last, 0.995, 0.95, stats=stats)
-        g1.record()
-        raw = adv.clone()
-        for _ in range(reps):
-            M.normalize_advantages(adv, stats=stats)         # all-reduces the 24-byte statistics when world > 1
-        g2.record()
+        if world == 1:
+            # replayed as CUDA graphs of `reps` launches each: the ~100 us / ~40 us kernels are timed without the
+            # Python wrapper's per-call work
+            gs_, gn_ = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
+            with torch.cuda.graph(gs_):
+                for _ in range(reps):
+                    scan_once()
+            with torch.cuda.graph(gn_):
+                for _ in range(reps):
+                    norm_once()
+            torch.cuda.synchronize()
+            g0.record()
+            gs_.replay()
+            g1.record()
+            gn_.replay()
+            g2.record()
+        else:
+            g0.record()
+            for _ in range(reps):
+                scan_once()
+            g1.record()
+            for _ in range(reps):
+                norm_once()
+            g2.record()
         torch.cuda.synchronize()
         scan_ms, norm_ms = g0.elapsed_time(g1) / reps, g1.elapsed_time(g2) / reps
         gae_info = {"num_steps": T, "num_envs": B, "scan_ms": scan_ms, "normalize_ms": norm_ms,
@@ -574,13 +619,16 @@ def main_ours(args):
                             "adv 4 + target 4, advantage statistics accumulated in the same pass; normalisation = "
                             "one in-place map (8 B)" + ("; with world > 1 normalize_ms includes the NCCL all-reduce "
                                                         "of (count, sum, sum of squares)" if world > 1 else "")}
-        if world > 1:
+        if world > 1 and Bg % world == 0:
             # self-check of the sharded normalisation: gather every rank's raw advantages on rank 0 and compare
             # the sharded result with the full-batch computation
+            stats.zero_()
+            M.calculate_gae(g_reward, g_done, g_value, g_last, 0.995, 0.95, stats=stats, out=(adv, tgt))
+            raw = adv.clone()
             M.normalize_advantages(raw, stats=stats)
             parts = [torch.empty_like(g_value) for _ in range(world)] if rank == 0 else None
             raws = [torch.empty_like(g_value) for _ in range(world)] if rank == 0 else None
-            adv2, _ = M.calculate_gae(g_reward, g_done, g_value, g_last, 0.995, 0.95)
+            adv2 = adv
             dist.gather(raw, parts, dst=0)
             dist.gather(adv2, raws, dst=0)
             if rank == 0:
@@ -668,7 +716,10 @@ def main_ours(args):
                                    f"env g starts at step g mod {MAX_STEPS}), action_mode 0",
                        "envs_global": Bg, "envs_per_gpu": B, "problems": P,
                        "group_threads": d.group_threads,
-                       "launch": f"CUDA graph of {G} steps" if graph is not None else "one kernel launch per step",
+                       "launch": {"step": "one kernel launch per step (msat_rollout_step)",
+                                  "graph": f"one kernel launch per step, replayed as CUDA graphs of {G} steps",
+                                  "multi": f"msat_rollout_steps: {G} steps per launch, observations of every step "
+                                           f"written to [K,B,A,D]"}[mode],
                        "l2": f"no flush: each step writes {B * A * env.obs_dim * 4 / 1e6:.0f} MB of observations per GPU "
                              f"(> 126 MB L2) and cycles {ACTION_CYCLE} action batches"
                              if B * A * env.obs_dim * 4 > 126e6 else
@@ -755,9 +806,11 @@ def parse_args(argv=None):
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-gae", action="store_true")
     ap.add_argument("--no-gnn-leg", action="store_true")
+    ap.add_argument("--launch", choices=["auto", "step", "graph", "multi"], default="auto",
+                    help="how the timed rollout steps are launched: one launch per step, CUDA graphs of 32 steps, or "
+                         "32 fused steps per launch (msat_rollout_steps); auto picks by per-GPU batch size")
     ap.add_argument("--graph", type=int, default=-1, metavar="G",
-                    help="replay the rollout steps as CUDA graphs of G steps each (0 = plain launches; default -1 = "
-                         "32-step graphs when a GPU owns <= 16,384 envs, plain launches above)")
+                    help="G > 0: CUDA graphs of G steps each; 0: never use graphs; default -1: follow --launch")
     ap.add_argument("--no-reset-legs", action="store_true")
     ap.add_argument("--no-kstep-leg", action="store_true")
     ap.add_argument("--gae-steps", type=int, default=512, help="T of the GAE leg (configs/MAPPO_CONFIG.yaml NUM_STEPS)")

@@ -156,6 +156,8 @@ int msat_plan_create(msat_plan** out, int32_t n, int32_t m, int32_t k, int32_t A
     while (gs < 256 && (long long)L.total * (kCtaThreads / gs) + kChain > kMaxSmem) gs *= 2;
     if ((long long)L.total * (kCtaThreads / gs) + kChain > kMaxSmem) { delete p; return MSAT_EUNSUPPORTED; }
     p->group_threads = gs;
+    p->layout_obs = L;
+    p->layout_noobs = group_layout(d, false);
     p->group_smem_bytes = L.total;
     p->smem_bytes = L.total * (kCtaThreads / gs);
     // launches that write no observations (emit_obs off, GNN-input mode) have ~m clause evaluations of work per

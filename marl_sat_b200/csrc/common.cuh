@@ -21,7 +21,9 @@ struct Dims {
 // State record word offsets (after the aw assignment words).
 enum { ST_STEP = 0, ST_PIDX = 1, ST_NUNSAT = 2, ST_FLAGS = 3 };
 
-constexpr uint16_t LIT_PAD = 0xFFFFu;   // literal code of a 0-padding literal (never true)
+// Literal code of a 0-padding literal (never true): one past the last real code (var << 1 | negated), so that
+// the per-env literal truth table tt[code] (2n + 1 bytes, tt[2n] = 0) answers it without a special case.
+__host__ __device__ __forceinline__ uint32_t lit_pad(const Dims& d) { return 2u * (uint32_t)d.n; }
 
 // Literal codes are stored literal-major ([k][m]) inside a bank record: consecutive lanes = consecutive
 // clauses read consecutive u16 (conflict-free shared-memory loads).

@@ -103,23 +103,42 @@ __global__ void __launch_bounds__(32 * S) gae_kernel(const float* __restrict__ r
 }
 
 // ---- software-pipelined plain scan (S = 1) ------------------------------------------------------------
-// When the batch alone fills the GPU (one thread per env column, ~14 warps per SM at 65,536 envs) the
-// limiter of the register-chunked scan above is latency: a warp's loads and its dependent chain do not
-// overlap.  Here every warp owns a private ring of GP_NS stages x GP_CH time steps in shared memory that
-// it fills with 16-byte cp.async (LDGSTS) copies -- reward / value rows of its 32 columns (128 B each) and
-// the done row (32 B) -- GP_NS-1 stages ahead of the chain, so ~7 KB per warp are in flight at any time
-// without holding registers.  No cross-warp synchronisation; the arithmetic is gae_segment's.
-constexpr int GP_CH = 8;                    // time steps per stage (multiple of 4, <= 16)
+// When the batch alone fills the GPU the register-chunked scan above stops at ~0.78 of the copy bandwidth:
+// not for lack of loads in flight but because every warp request covers only 128 contiguous bytes of a
+// [T, B] row, so HBM pages are opened for half-page bursts.  Here a lane owns FOUR adjacent env columns:
+// every warp instruction moves 512 contiguous bytes (16-byte cp.async / LDS.128 / STG.128; the done row as
+// 4-byte copies), the two warps of a CTA cover 1 KB of each row, and a private ring of GP_NS stages x
+// GP_CH time steps per warp keeps ~27 KB per warp in flight without holding registers.  Four independent
+// recurrences per lane give the instruction-level parallelism that the lower warp count takes away.  No
+// cross-warp synchronisation; per column the arithmetic (and its rounding order) is gae_segment's.
+constexpr int GP_CH = 8;                    // time steps per stage
 constexpr int GP_NS = 4;                    // ring depth
-constexpr int GP_STAGE = GP_CH * (128 + 128 + 32);
-constexpr int GP_WARPS = 4;
+constexpr int GP_COLS = 128;                // columns per warp (4 per lane)
+constexpr int GP_STAGE = GP_CH * (GP_COLS * 4 + GP_COLS * 4 + GP_COLS);
+constexpr int GP_WARPS = 2;
 
 __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem_dst)), "l"(gmem_src) : "memory");
 }
+__device__ __forceinline__ void cp_async4(void* smem_dst, const void* gmem_src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(smem_dst)), "l"(gmem_src) : "memory");
+}
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+__device__ __forceinline__ void gae_update(float r, float v, uint32_t dn, float gamma, float gl, float& next_value,
+                                           float& gae, double& ssum, double& ssq, float& adv, float& tgt) {
+    const float nt = dn ? 0.0f : 1.0f;
+    const float cc = __fmul_rn(gl, nt);
+    const float delta = __fsub_rn(__fadd_rn(r, __fmul_rn(__fmul_rn(gamma, next_value), nt)), v);
+    gae = __fadd_rn(delta, __fmul_rn(cc, gae));
+    ssum += (double)gae;
+    ssq += (double)gae * (double)gae;
+    adv = gae;
+    tgt = __fadd_rn(gae, v);                               // learner:526
+    next_value = v;
+}
 
 __global__ void __launch_bounds__(32 * GP_WARPS) gae_pipe_kernel(const float* __restrict__ reward, long long rs_t,
                                                                  const uint8_t* __restrict__ done,
@@ -130,81 +149,72 @@ __global__ void __launch_bounds__(32 * GP_WARPS) gae_pipe_kernel(const float* __
                                                                  double* __restrict__ stats) {
     extern __shared__ __align__(16) uint8_t gp_smem[];
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    const int b0 = (blockIdx.x * GP_WARPS + w) * 32;
-    if (b0 >= B) return;                                   // whole warp leaves
+    const int b = (blockIdx.x * GP_WARPS + w) * GP_COLS + 4 * lane;      // first of this lane's four columns
+    if (b - 4 * lane >= B) return;                         // whole warp leaves
     uint8_t* ring = gp_smem + (size_t)w * (GP_NS * GP_STAGE);
-    const int b = b0 + lane;
-    const bool ok = b < B;
+    const bool ok = b < B;                                 // B % 4 == 0: all four columns or none
     const int nchunks = (T + GP_CH - 1) / GP_CH;
 
-    // chunk c = time steps T-1-c*GP_CH, ..., down to T-c*GP_CH-GP_CH (row i of the stage = step t_hi - i)
+    // chunk c = time steps T-1-c*GP_CH down to T-c*GP_CH-GP_CH; row i of a stage = step t_hi - i
     auto issue = [&](int c) {
-        if (c < nchunks) {
+        if (c < nchunks && ok) {
             uint8_t* st = ring + (c % GP_NS) * GP_STAGE;
             const int t_hi = T - 1 - c * GP_CH;
-            const int piece = lane & 7, col = b0 + piece * 4;
 #pragma unroll
-            for (int j = 0; j < GP_CH / 4; ++j) {
-                const int i = (lane >> 3) + 4 * j, t = t_hi - i;
-                if (t >= 0 && col < B) {
-                    cp_async16(st + i * 128 + piece * 16, reward + (long long)t * rs_t + col);
-                    cp_async16(st + GP_CH * 128 + i * 128 + piece * 16, value + (size_t)t * B + col);
+            for (int i = 0; i < GP_CH; ++i) {
+                const int t = t_hi - i;
+                if (t >= 0) {
+                    cp_async16(st + i * (GP_COLS * 4) + lane * 16, reward + (long long)t * rs_t + b);
+                    cp_async16(st + GP_CH * GP_COLS * 4 + i * (GP_COLS * 4) + lane * 16, value + (size_t)t * B + b);
+                    cp_async4(st + 2 * GP_CH * GP_COLS * 4 + i * GP_COLS + lane * 4, done + (size_t)t * B + b);
                 }
             }
-            const int i = lane >> 1, t = t_hi - i, dcol = b0 + (lane & 1) * 16;
-            if (i < GP_CH && t >= 0 && dcol < B)
-                cp_async16(st + GP_CH * 256 + i * 32 + (lane & 1) * 16, done + (size_t)t * B + dcol);
         }
         cp_async_commit();                                 // one group per call keeps the group count uniform
     };
 
 #pragma unroll
     for (int c = 0; c < GP_NS - 1; ++c) issue(c);
-    float next_value = ok ? __ldg(last_val + b) : 0.0f;
-    float gae = 0.0f;
-    double ssum = 0.0, ssq = 0.0;
+    float nv[4] = {0.f, 0.f, 0.f, 0.f}, gae[4] = {0.f, 0.f, 0.f, 0.f};
+    if (ok) {
+        const float4 lv = *reinterpret_cast<const float4*>(last_val + b);
+        nv[0] = lv.x; nv[1] = lv.y; nv[2] = lv.z; nv[3] = lv.w;
+    }
+    double ssum[4] = {0.0, 0.0, 0.0, 0.0}, ssq[4] = {0.0, 0.0, 0.0, 0.0};
     for (int c = 0; c < nchunks; ++c) {
         issue(c + GP_NS - 1);
-        cp_async_wait<GP_NS - 1>();                        // chunk c has landed (this thread's copies) ...
-        __syncwarp();                                      // ... and every other lane's
+        cp_async_wait<GP_NS - 1>();                        // chunk c has landed: every lane reads only its own copies
         const uint8_t* st = ring + (c % GP_NS) * GP_STAGE;
-        const float* sr = reinterpret_cast<const float*>(st);
-        const float* sv = reinterpret_cast<const float*>(st + GP_CH * 128);
-        const uint8_t* sd = st + GP_CH * 256;
         const int t_hi = T - 1 - c * GP_CH;
-        float r[GP_CH], v[GP_CH];
-        uint8_t dn[GP_CH];
+        if (ok) {
 #pragma unroll
-        for (int i = 0; i < GP_CH; ++i) {
-            r[i] = sr[i * 32 + lane];
-            v[i] = sv[i * 32 + lane];
-            dn[i] = sd[i * 32 + lane];
-        }
-#pragma unroll
-        for (int i = 0; i < GP_CH; ++i) {
-            const int t = t_hi - i;
-            if (t >= 0 && ok) {
-                const float nt = dn[i] ? 0.0f : 1.0f;
-                const float cc = __fmul_rn(gl, nt);
-                const float delta = __fsub_rn(__fadd_rn(r[i], __fmul_rn(__fmul_rn(gamma, next_value), nt)), v[i]);
-                gae = __fadd_rn(delta, __fmul_rn(cc, gae));
-                ssum += (double)gae;
-                ssq += (double)gae * (double)gae;
-                __stcs(adv + (size_t)t * B + b, gae);
-                __stcs(targets + (size_t)t * B + b, __fadd_rn(gae, v[i]));        // learner:526
-                next_value = v[i];
+            for (int i = 0; i < GP_CH; ++i) {
+                const int t = t_hi - i;
+                if (t >= 0) {
+                    const float4 r4 = *reinterpret_cast<const float4*>(st + i * (GP_COLS * 4) + lane * 16);
+                    const float4 v4 = *reinterpret_cast<const float4*>(st + GP_CH * GP_COLS * 4 + i * (GP_COLS * 4) + lane * 16);
+                    const uint32_t d4 = *reinterpret_cast<const uint32_t*>(st + 2 * GP_CH * GP_COLS * 4 + i * GP_COLS + lane * 4);
+                    float4 a4, g4;
+                    gae_update(r4.x, v4.x, d4 & 0xFFu, gamma, gl, nv[0], gae[0], ssum[0], ssq[0], a4.x, g4.x);
+                    gae_update(r4.y, v4.y, d4 & 0xFF00u, gamma, gl, nv[1], gae[1], ssum[1], ssq[1], a4.y, g4.y);
+                    gae_update(r4.z, v4.z, d4 & 0xFF0000u, gamma, gl, nv[2], gae[2], ssum[2], ssq[2], a4.z, g4.z);
+                    gae_update(r4.w, v4.w, d4 & 0xFF000000u, gamma, gl, nv[3], gae[3], ssum[3], ssq[3], a4.w, g4.w);
+                    __stcs(reinterpret_cast<float4*>(adv + (size_t)t * B + b), a4);
+                    __stcs(reinterpret_cast<float4*>(targets + (size_t)t * B + b), g4);
+                }
             }
         }
-        __syncwarp();                                      // the stage is refilled by the next issue()
+        // the stage is refilled by this lane's own copies only after its reads above (program order)
     }
     if (stats) {
+        double s1 = (ssum[0] + ssum[1]) + (ssum[2] + ssum[3]), s2 = (ssq[0] + ssq[1]) + (ssq[2] + ssq[3]);
         for (int o = 16; o > 0; o >>= 1) {
-            ssum += __shfl_xor_sync(0xffffffffu, ssum, o);
-            ssq += __shfl_xor_sync(0xffffffffu, ssq, o);
+            s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+            s2 += __shfl_xor_sync(0xffffffffu, s2, o);
         }
         if (lane == 0) {
-            atomicAdd(&stats[1], ssum);
-            atomicAdd(&stats[2], ssq);
+            atomicAdd(&stats[1], s1);
+            atomicAdd(&stats[2], s2);
             if (blockIdx.x == 0 && w == 0) atomicAdd(&stats[0], (double)T * (double)B);
         }
     }
@@ -289,13 +299,25 @@ cudaError_t launch_gae(const float* reward, long long rs_t, long long rs_b, cons
     while (S < 32 && grid * S < 148 * 8 && T / (2 * S) >= GAE_CHUNK) S *= 2;
     const int seg_len = (T + S - 1) / S;
     // the batch fills the GPU by itself and the rows are 16-byte copyable: pipelined plain scan
-    const bool rows16 = rs_b == 1 && (rs_t % 4) == 0 && (B % 16) == 0 &&
+    const bool rows16 = rs_b == 1 && (rs_t % 4) == 0 && (B % 4) == 0 &&
                         ((reinterpret_cast<uintptr_t>(reward) | reinterpret_cast<uintptr_t>(value) |
-                          reinterpret_cast<uintptr_t>(done)) & 15) == 0;
+                          reinterpret_cast<uintptr_t>(last_val) | reinterpret_cast<uintptr_t>(adv) |
+                          reinterpret_cast<uintptr_t>(targets)) & 15) == 0 &&
+                        (reinterpret_cast<uintptr_t>(done) & 3) == 0;
     if (S == 1 && rows16 && !g_gae_force_plain) {
-        const int pgrid = (B + 32 * GP_WARPS - 1) / (32 * GP_WARPS);
-        gae_pipe_kernel<<<pgrid, 32 * GP_WARPS, GP_WARPS * GP_NS * GP_STAGE, s>>>(reward, rs_t, done, value, last_val,
-                                                                                gamma, gl, adv, targets, T, B, stats);
+        constexpr int kSmem = GP_WARPS * GP_NS * GP_STAGE;
+        static std::atomic<unsigned long long> prepared{0};
+        int dev = 0;
+        cudaError_t err = cudaGetDevice(&dev);
+        if (err != cudaSuccess) return err;
+        if (!(prepared.load(std::memory_order_acquire) & (1ULL << (dev & 63)))) {
+            err = cudaFuncSetAttribute((const void*)gae_pipe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem);
+            if (err != cudaSuccess) return err;
+            prepared.fetch_or(1ULL << (dev & 63), std::memory_order_release);
+        }
+        const int pgrid = (B + GP_COLS * GP_WARPS - 1) / (GP_COLS * GP_WARPS);
+        gae_pipe_kernel<<<pgrid, 32 * GP_WARPS, kSmem, s>>>(reward, rs_t, done, value, last_val, gamma, gl, adv, targets,
+                                                            T, B, stats);
         return cudaGetLastError();
     }
 #define MSAT_GAE_LAUNCH(SS)                                                                                         \

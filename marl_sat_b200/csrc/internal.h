@@ -4,6 +4,40 @@
 
 #include "common.cuh"
 
+namespace msat {
+
+constexpr int kCtaThreads = 256;
+constexpr int kMaxSmemOptin = 227 * 1024;
+
+// Shared-memory carve-up of one env group (byte offsets from the group base).  Launches that write
+// observations stage the whole bank record (literals + agent-mask stream) and need the value / mask
+// re-basing buffers; launches without observations stage only the literal block and keep the per-clause
+// true-literal counts for the GNN features, so eight one-warp groups fit in ~26 KB per CTA.
+struct GroupLayout {
+    int rec, st, satw, satw_old, x, smx, tt, stage, bar, misc, total;
+};
+constexpr int kCfStageBytes = 12 * 256 + 16;      // clause-feature staging of eval_clauses_gnn (256 clauses per pass)
+inline GroupLayout group_layout(const Dims& d, bool obs) {
+    GroupLayout L;
+    int o = 0;
+    L.rec = o;  o += obs ? d.rec_bytes : ((d.lits_bytes + 127) & ~127);   // TMA destination, 128-byte aligned
+    L.st = o;   o += 4 * d.state_words;           // state record (multiple of 16 bytes)
+    L.stage = o; o += obs ? 0 : kCfStageBytes;    // 16-byte aligned (rec and state sizes are multiples of 16)
+    L.satw = o; o += 4 * d.sw;
+    L.satw_old = o; o += 4 * d.sw;                // clause status before the flips (shaped-reward mode only)
+    L.x = o;    o += obs ? 4 * d.xw : 0;
+    L.tt = o;   o += ((2 * d.n + 4) & ~3) + 4;    // literal truth table: 2n + 1 bytes, written as 32-bit words
+    o = (o + 7) & ~7;
+    L.smx = o;  o += obs ? 8 * (d.fw + 2) : 0;    // {mask word, value word} per 32 observation ints
+    L.bar = o;  o += 8;                           // mbarrier
+    L.misc = o; o += 16 + 64;                     // [0] #unsatisfied accumulator, [1] new problem idx, [2..3] reset key,
+                                                  // then float[16]: n_true / 3.0 table of the GNN clause features
+    L.total = (o + 127) & ~127;
+    return L;
+}
+
+}  // namespace msat
+
 struct msat_plan {
     msat::Dims d;
     int group_threads;     // GS: threads cooperating on one env (32/64/128/256)
@@ -11,6 +45,7 @@ struct msat_plan {
     int smem_bytes;        // dynamic shared memory per 256-thread CTA
     int group_threads_noobs;   // GS used when a launch writes no observations (little per-env work: small groups)
     int smem_bytes_noobs;
+    msat::GroupLayout layout_obs, layout_noobs;   // shared-memory carve-up of one env group, computed once
     int compile_smem_bytes;
     int reward_mode = 0;       // MSAT_REWARD_SPARSE / MSAT_REWARD_SHAPED (msat_plan_set_reward)
     float r_gamma = 0.99f, r_clause = 0.02f, r_sat = 1.0f;
@@ -22,38 +57,10 @@ struct msat_plan {
 
 namespace msat {
 
-constexpr int kCtaThreads = 256;
-constexpr int kMaxSmemOptin = 227 * 1024;
-
-// Shared-memory carve-up of one env group (byte offsets from the group base).  Launches that write
-// observations stage the whole bank record (literals + agent-mask stream) and need the value / mask
-// re-basing buffers; launches without observations stage only the literal block and keep the per-clause
-// true-literal counts for the GNN features, so eight one-warp groups fit in ~26 KB per CTA.
-struct GroupLayout {
-    int rec, st, satw, satw_old, x, smx, ntrue, bar, misc, total;
-};
-__host__ __device__ inline GroupLayout group_layout(const Dims& d, bool obs) {
-    GroupLayout L;
-    int o = 0;
-    L.rec = o;  o += obs ? d.rec_bytes : ((d.lits_bytes + 127) & ~127);   // TMA destination, 128-byte aligned
-    L.st = o;   o += 4 * d.state_words;           // state record (multiple of 16 bytes)
-    L.satw = o; o += 4 * d.sw;
-    L.satw_old = o; o += 4 * d.sw;                // clause status before the flips (shaped-reward mode only)
-    L.x = o;    o += obs ? 4 * d.xw : 0;
-    o = (o + 7) & ~7;
-    L.smx = o;  o += obs ? 8 * (d.fw + 2) : 0;    // {mask word, value word} per 32 observation ints
-    L.ntrue = o; o += obs ? 0 : ((d.m + 3) & ~3); // true literals per clause (u8), GNN clause features
-    o = (o + 7) & ~7;
-    L.bar = o;  o += 8;                           // mbarrier
-    L.misc = o; o += 16 + 64;                     // [0] #unsatisfied accumulator, [1] new problem idx, [2..3] reset key,
-                                                  // then float[16]: n_true / 3.0 table of the GNN clause features
-    L.total = (o + 127) & ~127;
-    return L;
-}
-
 constexpr int kMaxFusedSteps = 64;                // K of msat_rollout_steps
 
 struct EnvArgs {
+    GroupLayout L;              // filled in by launch_env from the plan
     const uint8_t* bank;
     int P;
     const uint32_t* state_in;

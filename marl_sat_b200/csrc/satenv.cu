@@ -23,7 +23,7 @@ __global__ void __launch_bounds__(256) compile_bank_kernel(Dims d, const int32_t
     uint32_t* mflat = reinterpret_cast<uint32_t*>(rec + d.lits_bytes);
 
     for (int i = tid; i < (d.m + d.n) * d.agw; i += nt) csm[i] = 0u;
-    for (int i = d.m * d.k + tid; i < d.lits_bytes / 2; i += nt) lits[i] = LIT_PAD;
+    for (int i = d.m * d.k + tid; i < d.lits_bytes / 2; i += nt) lits[i] = lit_pad(d);
     for (int i = d.lits_bytes / 4 + d.fw + 1 + tid; i < d.rec_bytes / 4; i += nt)
         reinterpret_cast<uint32_t*>(rec)[i] = 0u;
     __syncthreads();
@@ -36,7 +36,7 @@ __global__ void __launch_bounds__(256) compile_bank_kernel(Dims d, const int32_t
             if (lit == 0) {
                 // env:100,106: |0|-1 = -1 equals the -1 padding of every agent that owns fewer than
                 // V variables, so the clause becomes "related" to all of those agents.
-                code = LIT_PAD;
+                code = lit_pad(d);
                 if (d.rem > 0)
                     for (int a = d.rem; a < d.A; ++a) ca[a >> 5] |= 1u << (a & 31);
             } else {
@@ -54,7 +54,7 @@ __global__ void __launch_bounds__(256) compile_bank_kernel(Dims d, const int32_t
     for (int c = tid; c < d.m; c += nt) {
         for (int j = 0; j < d.k; ++j) {
             const uint16_t code = lits[lit_index(d.m, c, j)];
-            if (code == LIT_PAD) continue;
+            if (code == lit_pad(d)) continue;
             const int v = code >> 1;
             for (int w = 0; w < d.agw; ++w) {
                 const uint32_t x = clause_agents[c * d.agw + w];
@@ -88,62 +88,126 @@ __global__ void __launch_bounds__(256) compile_bank_kernel(Dims d, const int32_t
 // Device pieces of the env kernel.  One group of GS threads owns one env.
 // =====================================================================================
 
-// Clause truth via warp ballots (env:130-156): lane = clause, ballot word = 32 clause-status bits.
-// One literal: true <=> assignment bit != negation flag; a 0 padding literal is never true (env:141-144).
-__device__ __forceinline__ bool literal_true(uint32_t code, const uint32_t* assign) {
-    const uint32_t v = code >> 1;
-    return code != LIT_PAD && (((assign[v >> 5] >> (v & 31)) ^ code) & 1u) != 0u;
-}
-template <int K>
-__device__ __forceinline__ bool clause_true_fixed(const uint16_t* lits, int m, int c, const uint32_t* assign) {
-    uint32_t code[K];
-#pragma unroll
-    for (int j = 0; j < K; ++j) code[j] = lits[lit_index(m, c, j)];     // independent loads first
-    bool sat = false;
-#pragma unroll
-    for (int j = 0; j < K; ++j) sat |= literal_true(code[j], assign);
-    return sat;
+// Literal truth table of the current assignment: tt[code] for code = (var << 1) | negated, i.e. tt[2v] = a_v,
+// tt[2v+1] = !a_v, and tt[2n] = 0 for the 0-padding literal (never true, env:141-144).  2n + 1 bytes per
+// env, rebuilt after every change of the assignment; it turns one literal evaluation into one byte load.
+template <int GS>
+__device__ __forceinline__ void build_truth_table(const Dims& d, const uint32_t* assign, uint8_t* tt, int gt) {
+    const int n2 = 2 * d.n;
+    for (int w = gt; 4 * w <= n2; w += GS) {          // four codes (two variables) per 32-bit store
+        const int v = 2 * w;
+        const uint32_t word = assign[v >> 5] >> (v & 31);      // v is even: v and v+1 sit in the same word
+        const uint32_t a0 = word & 1u, a1 = (word >> 1) & 1u;
+        uint32_t b = a0 | ((a0 ^ 1u) << 8) | (a1 << 16) | ((a1 ^ 1u) << 24);
+        if (v >= d.n) b = 0u;                                   // codes 2n .. : padding literal
+        else if (v + 1 >= d.n) b &= 0x0000FFFFu;
+        reinterpret_cast<uint32_t*>(tt)[w] = b;
+    }
 }
 
-// NT: also store the number of true literals per clause (u8) for the GNN clause features (learner:177-185).
-template <int GS, bool NT>
-__device__ __forceinline__ void eval_clauses(const Dims& d, const uint16_t* lits, const uint32_t* assign,
-                                             uint32_t* satw, uint8_t* ntrue, int* nunsat, int gt) {
+// Clause truth via warp ballots (env:130-156): lane = clause, ballot word = 32 clause-status bits,
+// __popc for the number of unsatisfied clauses.
+template <int GS>
+__device__ __forceinline__ void eval_clauses(const Dims& d, const uint16_t* lits, const uint8_t* tt, uint32_t* satw,
+                                             int* nunsat, int gt) {
     const int lane = gt & 31;
     int local = 0;
     for (int w = gt >> 5; w < d.sw; w += GS / 32) {
         const int c = w * 32 + lane;
         const bool valid = c < d.m;
-        bool sat = false;
+        uint32_t cnt = 0u;
         if (valid) {
-            if (NT) {
-                int cnt = 0;
-                if (d.k == 3) {
-                    uint32_t code[3];
-#pragma unroll
-                    for (int j = 0; j < 3; ++j) code[j] = lits[lit_index(d.m, c, j)];
-#pragma unroll
-                    for (int j = 0; j < 3; ++j) cnt += literal_true(code[j], assign) ? 1 : 0;
-                } else {
-#pragma unroll 4
-                    for (int j = 0; j < d.k; ++j) cnt += literal_true(lits[lit_index(d.m, c, j)], assign) ? 1 : 0;
-                }
-                ntrue[c] = (uint8_t)cnt;
-                sat = cnt > 0;
-            } else if (d.k == 3) {
-                sat = clause_true_fixed<3>(lits, d.m, c, assign);
+            if (d.k == 3) {
+                const uint32_t c0 = lits[c], c1 = lits[d.m + c], c2 = lits[2 * d.m + c];   // independent loads first
+                cnt = tt[c0] | tt[c1] | tt[c2];
             } else {
 #pragma unroll 4
-                for (int j = 0; j < d.k; ++j) sat |= literal_true(lits[lit_index(d.m, c, j)], assign);
+                for (int j = 0; j < d.k; ++j) cnt |= tt[lits[lit_index(d.m, c, j)]];
             }
         }
-        const uint32_t word = __ballot_sync(0xffffffffu, valid && sat);
+        const uint32_t word = __ballot_sync(0xffffffffu, cnt != 0u);
         if (lane == 0) {
             satw[w] = word;
             if (nunsat) local += min(32, d.m - w * 32) - __popc(word);
         }
     }
     if (nunsat && lane == 0 && local) atomicAdd(nunsat, local);
+}
+
+// ---- bulk (TMA) store shared -> global ----------------------------------------------------------------
+__device__ __forceinline__ void tma_store_1d(void* gmem_dst, const void* smem_src, uint32_t bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gmem_dst), "r"(smem_u32(smem_src)),
+                 "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+// all committed bulk stores of this thread have finished READING their shared-memory source
+__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+
+// Clause evaluation for a GNN-style consumer (learner:165-195): besides status bits and the unsatisfied
+// count it emits clause_features float[m][3] = {is_sat, #true literals / 3.0, 1} -- the literal 3.0 of
+// learner:185 for every clause width.  The floats of up to kCfStageClauses clauses are staged in shared
+// memory (lane = clause, three conflict-free 4-byte stores) at the same 16-byte phase as their global
+// destination and leave as ONE bulk (TMA) store per pass; the <= 3 floats before / after the 16-byte
+// aligned body go out as scalars.  cf1[t] = t / 3.0 for t = 0..15.
+constexpr int kCfStageClauses = 256;
+template <int GS>
+__device__ __forceinline__ void eval_clauses_gnn(const Dims& d, const uint16_t* lits, const uint8_t* tt, uint32_t* satw,
+                                                 int* nunsat, const float* cf1, uint8_t* stage,
+                                                 float* __restrict__ cf_out, int gid, int gt) {
+    const int lane = gt & 31;
+    int local = 0;
+    constexpr int kRoundsPerPass = kCfStageClauses / 32;
+    for (int w0 = 0; w0 < d.sw; w0 += kRoundsPerPass) {
+        const int c0 = w0 * 32;
+        const int c1 = min(d.m, c0 + kCfStageClauses);
+        uint8_t* gdst = reinterpret_cast<uint8_t*>(cf_out + 3 * (size_t)c0);
+        const uint32_t phase16 = (uint32_t)(reinterpret_cast<uintptr_t>(gdst) & 15u);
+        float* sf = reinterpret_cast<float*>(stage + phase16);
+        if (w0 > 0) {
+            if (gt == 0) tma_store_wait_read();        // the previous pass has left the staging buffer
+            group_sync<GS>(gid);
+        }
+        for (int w = w0 + (gt >> 5); w < min(d.sw, w0 + kRoundsPerPass); w += GS / 32) {
+            const int c = w * 32 + lane;
+            const bool valid = c < d.m;
+            uint32_t cnt = 0u;
+            if (valid) {
+                if (d.k == 3) {
+                    const uint32_t l0 = lits[c], l1 = lits[d.m + c], l2 = lits[2 * d.m + c];
+                    cnt = (uint32_t)tt[l0] + tt[l1] + tt[l2];
+                } else {
+#pragma unroll 4
+                    for (int j = 0; j < d.k; ++j) cnt += tt[lits[lit_index(d.m, c, j)]];
+                }
+                float* o = sf + 3 * (c - c0);
+                o[0] = cnt ? 1.0f : 0.0f;
+                o[1] = cnt < 16u ? cf1[cnt] : __fdiv_rn((float)cnt, 3.0f);
+                o[2] = 1.0f;
+            }
+            const uint32_t word = __ballot_sync(0xffffffffu, cnt != 0u);
+            if (lane == 0) {
+                satw[w] = word;
+                local += min(32, d.m - w * 32) - __popc(word);
+            }
+        }
+        fence_proxy_async();                           // staged floats -> visible to the bulk-copy engine
+        group_sync<GS>(gid);
+        const uint32_t len = 12u * (uint32_t)(c1 - c0);
+        uint32_t head = (16u - phase16) & 15u;
+        head = head < len ? head : len;
+        const uint32_t body = (len - head) & ~15u;
+        if (gt == 0 && body) {
+            tma_store_1d(gdst + head, stage + phase16 + head, body);
+            tma_store_commit();
+        }
+        if (gt >= 1 && gt < 8) {                        // scalar head (lanes 1-3) and tail (lanes 4-6)
+            const uint32_t i = gt < 4 ? (uint32_t)(gt - 1) * 4u : head + body + (uint32_t)(gt - 4) * 4u;
+            const bool mine = gt < 4 ? i < head : i < len;
+            if (mine) *reinterpret_cast<float*>(gdst + i) = *reinterpret_cast<const float*>(stage + phase16 + i);
+        }
+    }
+    if (lane == 0 && local) atomicAdd(nunsat, local);
 }
 
 // assign = randint(key, (n,), 0, 2) (env:162): bit 0 of threefry_2x32(split(key)[1], arange(n)).
@@ -296,27 +360,12 @@ __device__ __forceinline__ void store_words_vec4(uint32_t* __restrict__ dst, int
     if (gt < 3 && i < count) dst[i] = f(i);
 }
 
-// Dynamic GNN input of the env's (post-reset) state straight from shared memory (learner:165-195):
-// assignment int32[n]; clause_features float[m][3] = {is_sat, #true literals / 3.0, 1} -- the literal 3.0 of
-// learner:185 for every clause width.  Lets a GNN-style consumer skip the local observations altogether
-// (SURVEY.md F8, section 8f rank 1).  `ntrue` holds the per-clause counts of the last evaluation; the
-// k+1 possible quotients are tabulated once per group (cf1), so the 3m floats leave as 16-byte stores.
+// Assignment part of the dynamic GNN input (learner:165): int32[n] per env as 16-byte stores.
 template <int GS>
-__device__ __forceinline__ void emit_gnn(const Dims& d, long long row, const uint8_t* ntrue, const float* cf1,
-                                         const uint32_t* assign, int32_t* __restrict__ gnn_assign,
-                                         float* __restrict__ gnn_cf, int gt) {
-    if (gnn_assign)
-        store_words_vec4<GS>(reinterpret_cast<uint32_t*>(gnn_assign) + row * d.n, d.n, gt,
-                             [&](int v) { return (assign[v >> 5] >> (v & 31)) & 1u; });
-    if (gnn_cf)
-        store_words_vec4<GS>(reinterpret_cast<uint32_t*>(gnn_cf) + row * d.m * 3, 3 * d.m, gt, [&](int i) {
-            const int c = (int)(((uint32_t)i * 43691u) >> 17);        // i / 3 for i < 98304
-            const int comp = i - 3 * c;
-            const int nt = ntrue[c];
-            const float v = comp == 0 ? (nt > 0 ? 1.0f : 0.0f)
-                                      : (comp == 1 ? (nt < 16 ? cf1[nt] : __fdiv_rn((float)nt, 3.0f)) : 1.0f);
-            return __float_as_uint(v);
-        });
+__device__ __forceinline__ void emit_gnn_assignment(const Dims& d, long long row, const uint32_t* assign,
+                                                    int32_t* __restrict__ gnn_assign, int gt) {
+    store_words_vec4<GS>(reinterpret_cast<uint32_t*>(gnn_assign) + row * d.n, d.n, gt,
+                         [&](int v) { return (assign[v >> 5] >> (v & 31)) & 1u; });
 }
 
 // One rollout step of the rng alone (learner:397,416,426): rng <- split(rng)[0]; rng <- split(rng)[0];
@@ -338,12 +387,12 @@ __device__ __forceinline__ void rng_advance(uint32_t& r0, uint32_t& r1) {
 // staged, observation re-basing buffers); !OBS = literal block only, optional GNN-input outputs.
 // =====================================================================================
 template <int GS, int MODE, bool OBS, bool MULTI>
-__global__ void __launch_bounds__(kCtaThreads, MULTI ? 4 : 8) env_kernel(const Dims d, const EnvArgs a) {
+__global__ void __launch_bounds__(kCtaThreads, (MULTI || !OBS) ? 4 : 8) env_kernel(const Dims d, const EnvArgs a) {
     extern __shared__ __align__(128) uint8_t smem_raw[];
     constexpr int NG = kCtaThreads / GS;
     const int gid = threadIdx.x / GS, gt = threadIdx.x % GS;
     const int e = blockIdx.x * NG + gid;
-    const GroupLayout L = group_layout(d, OBS);
+    const GroupLayout& L = a.L;
     const int K = MULTI ? a.num_steps : 1;          // MULTI only with MODE_STEP
 
     // ---- K > 1 with fused keys: the K chains {rng', act, step, prob, reset} of learner:397-434, once per CTA
@@ -375,14 +424,15 @@ __global__ void __launch_bounds__(kCtaThreads, MULTI ? 4 : 8) env_kernel(const D
     uint32_t* satw_old = reinterpret_cast<uint32_t*>(base + L.satw_old);
     uint32_t* X = reinterpret_cast<uint32_t*>(base + L.x);
     uint2* smx = reinterpret_cast<uint2*>(base + L.smx);
-    uint8_t* ntrue = base + L.ntrue;
+    uint8_t* tt = base + L.tt;
+    uint8_t* stage = base + L.stage;
     uint64_t* bar = reinterpret_cast<uint64_t*>(base + L.bar);
     int* misc = reinterpret_cast<int*>(base + L.misc);
     const uint16_t* lits = reinterpret_cast<const uint16_t*>(rec);
     const uint32_t* mflat = reinterpret_cast<const uint32_t*>(rec + d.lits_bytes);
     uint32_t* st_tail = st + d.aw;
     const uint32_t tma_bytes = OBS ? (uint32_t)d.rec_bytes : (uint32_t)d.lits_bytes;
-    const bool want_gnn = !OBS && (a.gnn_assign || a.gnn_cf);
+    const bool want_cf = !OBS && a.gnn_cf != nullptr;
     float* cf1 = reinterpret_cast<float*>(misc + 4);     // n_true / 3.0 for n_true = 0..15 (learner:185)
 
     // ---- stage the state record (plain loads) ----
@@ -396,7 +446,7 @@ __global__ void __launch_bounds__(kCtaThreads, MULTI ? 4 : 8) env_kernel(const D
         misc[0] = 0;
         mbar_init(bar, 1);
     }
-    if (want_gnn && gt < 16) cf1[gt] = __fdiv_rn((float)gt, 3.0f);
+    if (want_cf && gt < 16) cf1[gt] = __fdiv_rn((float)gt, 3.0f);
     group_sync<GS>(gid);
 
     // Every thread keeps its own copy of the scalar state fields in registers from here on: thread 0 rewrites
@@ -432,7 +482,9 @@ __global__ void __launch_bounds__(kCtaThreads, MULTI ? 4 : 8) env_kernel(const D
                 phase ^= 1u;
                 loaded_pidx = pidx;
             }
-            eval_clauses<GS, false>(d, lits, st, satw_old, nullptr, nullptr, gt);
+            build_truth_table<GS>(d, st, tt, gt);
+            group_sync<GS>(gid);
+            eval_clauses<GS>(d, lits, tt, satw_old, nullptr, gt);
             group_sync<GS>(gid);
         }
 
@@ -443,13 +495,17 @@ __global__ void __launch_bounds__(kCtaThreads, MULTI ? 4 : 8) env_kernel(const D
             apply_actions<GS>(d, a.actions + (long long)j * a.act_step_stride, e, st, gt);
         }
         group_sync<GS>(gid);
+        build_truth_table<GS>(d, st, tt, gt);
         if (loaded_pidx != pidx) {
             mbar_wait(bar, phase);
             phase ^= 1u;
             loaded_pidx = pidx;
         }
+        group_sync<GS>(gid);
 
-        eval_clauses<GS, !OBS>(d, lits, st, satw, ntrue, &misc[0], gt);
+        float* cf_row = (want_cf && emit) ? a.gnn_cf + row * d.m * 3 : nullptr;
+        if (cf_row) eval_clauses_gnn<GS>(d, lits, tt, satw, &misc[0], cf1, stage, cf_row, gid, gt);
+        else eval_clauses<GS>(d, lits, tt, satw, &misc[0], gt);
         group_sync<GS>(gid);
         nunsat = misc[0];
 
@@ -523,12 +579,22 @@ __global__ void __launch_bounds__(kCtaThreads, MULTI ? 4 : 8) env_kernel(const D
                 group_sync<GS>(gid);
                 threefry_assign<GS>(d, rk0, rk1, st, gt);
                 group_sync<GS>(gid);
+                build_truth_table<GS>(d, st, tt, gt);
                 if (pidx != loaded_pidx) {
                     mbar_wait(bar, phase);
                     phase ^= 1u;
                     loaded_pidx = pidx;
                 }
-                eval_clauses<GS, !OBS>(d, lits, st, satw, ntrue, &misc[0], gt);
+                group_sync<GS>(gid);
+                // the clause features of the finished episode are already on their way to the same rows: let
+                // those bulk stores complete before the new episode's features are sent after them
+                if (cf_row) {
+                    if (gt == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+                    group_sync<GS>(gid);
+                    eval_clauses_gnn<GS>(d, lits, tt, satw, &misc[0], cf1, stage, cf_row, gid, gt);
+                } else {
+                    eval_clauses<GS>(d, lits, tt, satw, &misc[0], gt);
+                }
                 group_sync<GS>(gid);
                 nunsat = misc[0];
                 step_cur = 0;
@@ -540,15 +606,18 @@ __global__ void __launch_bounds__(kCtaThreads, MULTI ? 4 : 8) env_kernel(const D
             nunsat_prev = nunsat;
         }
         if (emit) {
-            if (want_gnn) emit_gnn<GS>(d, row, ntrue, cf1, st, a.gnn_assign, a.gnn_cf, gt);
+            if (!OBS && a.gnn_assign) emit_gnn_assignment<GS>(d, row, st, a.gnn_assign, gt);
             if (OBS && a.obs) emit_obs<GS>(d, row, st, satw, X, smx, mflat, a.obs, gid, gt);
         }
         if (!last) {
+            if (cf_row && gt == 0) tma_store_wait_read();   // the staging buffer is rewritten by the next step
             group_sync<GS>(gid);           // every lane has read misc[0] / the state of this step
             if (gt == 0) misc[0] = 0;      // published by the barrier after the next step's flips
         }
     }
 
+    // a CTA must not retire while the bulk-copy engine still reads its shared memory
+    if (want_cf && gt == 0) tma_store_wait_read();
     if (MODE != MODE_OBS) {
         group_sync<GS>(gid);
         if (gt == 0) {
@@ -601,6 +670,7 @@ cudaError_t launch_env(const msat_plan* plan, EnvMode mode, const EnvArgs& a0, c
     EnvArgs a = a0;
     if (a.num_steps < 1) a.num_steps = 1;
     const bool noobs = a.obs == nullptr;
+    a.L = noobs ? plan->layout_noobs : plan->layout_obs;
     const int gs = noobs ? plan->group_threads_noobs : plan->group_threads;
     const int smem = noobs ? plan->smem_bytes_noobs : plan->smem_bytes;
     if (noobs) {
@@ -650,7 +720,7 @@ __global__ void __launch_bounds__(128) export_kernel(const Dims d, const ExportA
             bool sat = false;
             for (int j = 0; j < d.k; ++j) {
                 const uint32_t code = lits[lit_index(d.m, c, j)];
-                if (code != LIT_PAD) {
+                if (code != lit_pad(d)) {
                     const uint32_t v = code >> 1;
                     sat |= (((st[v >> 5] >> (v & 31)) ^ code) & 1u) != 0u;
                 }
@@ -667,7 +737,7 @@ __global__ void __launch_bounds__(128) export_kernel(const Dims d, const ExportA
     if (a.clauses || a.l2a)
         for (int i = tid; i < d.m * d.k; i += nt) {
             const uint32_t code = lits[lit_index(d.m, i / d.k, i % d.k)];
-            const int v = (code == LIT_PAD) ? -1 : (int)(code >> 1);
+            const int v = (code == lit_pad(d)) ? -1 : (int)(code >> 1);
             if (a.clauses) a.clauses[(size_t)e * d.m * d.k + i] = v < 0 ? 0 : ((code & 1u) ? -(v + 1) : (v + 1));
             // env:160: index -1 wraps to the last variable
             if (a.l2a) a.l2a[(size_t)e * d.m * d.k + i] = var_to_agent(d, v < 0 ? d.n - 1 : v);

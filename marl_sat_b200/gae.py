@@ -17,11 +17,15 @@ from .env import _ptr, _stream_ptr
 
 
 def calculate_gae(reward: torch.Tensor, done: torch.Tensor, value: torch.Tensor, last_val: torch.Tensor,
-                  gamma: float, gae_lambda: float, stats: Optional[torch.Tensor] = None) -> Tuple[torch.Tensor, torch.Tensor]:
+                  gamma: float, gae_lambda: float, stats: Optional[torch.Tensor] = None,
+                  out: Optional[Tuple[torch.Tensor, torch.Tensor]] = None) -> Tuple[torch.Tensor, torch.Tensor]:
     """reward f32 ``[T,B,A]`` (agent 0 is read, learner:514) or ``[T,B]``; done bool/uint8 ``[T,B]``;
     value f32 ``[T,B]``; last_val f32 ``[B]`` -> ``(advantages, targets)`` f32 ``[T,B]``
     (``targets = advantages + value`` with un-normalised advantages, learner:526).  ``stats`` (a zeroed
-    float64[3] device tensor) receives the advantages' (count, sum, sum of squares) from the same pass."""
+    float64[3] device tensor) receives the advantages' (count, sum, sum of squares) from the same pass.
+    Within one time segment the operation order is the reference's (no FMA contraction); when the batch is
+    too small to fill the GPU the time axis is split into segments whose affine maps are composed, which
+    changes the rounding sequence (still within the 1e-5 relative tolerance of the contract)."""
     lib = _lib.load()
     if not reward.is_cuda:
         raise RuntimeError("calculate_gae needs CUDA tensors: there is no CPU fallback")
@@ -48,8 +52,14 @@ def calculate_gae(reward: torch.Tensor, done: torch.Tensor, value: torch.Tensor,
     value = value.contiguous()
     last_val = last_val.contiguous()
     rs_t, rs_b = reward.stride(0), reward.stride(1)
-    adv = torch.empty((T, B), dtype=torch.float32, device=value.device)
-    tgt = torch.empty((T, B), dtype=torch.float32, device=value.device)
+    if out is not None:         # preallocated (advantages, targets): contiguous float32 [T, B]
+        adv, tgt = out
+        for t in (adv, tgt):
+            if tuple(t.shape) != (T, B) or t.dtype != torch.float32 or not t.is_contiguous() or t.device != value.device:
+                raise ValueError("out must be two contiguous float32 [T, B] tensors on the inputs' device")
+    else:
+        adv = torch.empty((T, B), dtype=torch.float32, device=value.device)
+        tgt = torch.empty((T, B), dtype=torch.float32, device=value.device)
     _lib.check(lib.msat_gae(_ptr(reward), rs_t, rs_b, _ptr(done), _ptr(value), _ptr(last_val), float(gamma),
                             float(gae_lambda), _ptr(adv), _ptr(tgt), _ptr(stats), T, B, _stream_ptr(value.device)),
                "msat_gae")
@@ -73,9 +83,13 @@ def normalize_advantages(adv: torch.Tensor, stats: Optional[torch.Tensor] = None
     if stats is not None and (stats.dtype != torch.float64 or stats.numel() != 3):
         raise ValueError("stats must be float64[3]")
     work = adv if adv.is_contiguous() else adv.contiguous()      # a strided view is normalised through a copy ...
-    stats = advantage_stats(work) if stats is None else stats.clone()
-    if torch.distributed.is_available() and torch.distributed.is_initialized() and \
-            torch.distributed.get_world_size(group) > 1:
+    distributed = torch.distributed.is_available() and torch.distributed.is_initialized() and \
+        torch.distributed.get_world_size(group) > 1
+    if stats is None:
+        stats = advantage_stats(work)
+    elif distributed:
+        stats = stats.clone()                                    # the caller's local statistics stay local
+    if distributed:
         torch.distributed.all_reduce(stats, op=torch.distributed.ReduceOp.SUM, group=group)
     _lib.check(lib.msat_adv_normalize(_ptr(work), work.numel(), _ptr(stats), _stream_ptr(work.device)),
                "msat_adv_normalize")
