@@ -366,6 +366,12 @@ def main_ours(args):
         sampler.start()
 
     # ---- device-resident throughput: `value` -------------------------------------------------
+    # bring the GPU to its steady clocks first (>= 60 ms of steps), then the W warm-up steps the caller asked for
+    t_pre = time.perf_counter()
+    while time.perf_counter() - t_pre < 0.06:
+        for i in range(8):
+            vec.step(actions[i])
+        torch.cuda.synchronize()
     for i in range(W):
         vec.step(actions[i % ACTION_CYCLE])
     torch.cuda.synchronize()

@@ -194,6 +194,7 @@ int msat_plan_set_reset_counter(msat_plan* plan, uint64_t* counter_dev) {
 int msat_tune(const char* key, int32_t value) {
     if (!key) return MSAT_EINVAL;
     if (!strcmp(key, "gae_plain")) { g_gae_force_plain = value; return MSAT_OK; }
+    if (!strcmp(key, "gae_variant")) { g_gae_variant = value; return MSAT_OK; }
     return MSAT_EINVAL;
 }
 
@@ -257,6 +258,7 @@ static int rollout_launch(const msat_plan* plan, const void* bank, int32_t P, co
     if (!rng_in || !chain_out || Bg <= 0 || env_offset < 0 || (long long)env_offset + B > Bg) return MSAT_EINVAL;
     if (Bg > (1 << 30)) return MSAT_EUNSUPPORTED;
     if (newly_satisfied && plan->reward_mode != MSAT_REWARD_SHAPED) return MSAT_EINVAL;
+    if (gnn_clause_features && plan->d.k > 15) return MSAT_EUNSUPPORTED;   // 16-entry feature table
     {   // the advanced chain is written while other CTAs still read rng_in: the buffers must not overlap
         const uintptr_t r = reinterpret_cast<uintptr_t>(rng_in), c = reinterpret_cast<uintptr_t>(chain_out);
         if (r + 8 > c && c + 40 > r) return MSAT_EINVAL;

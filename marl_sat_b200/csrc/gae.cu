@@ -111,11 +111,8 @@ __global__ void __launch_bounds__(32 * S) gae_kernel(const float* __restrict__ r
 // GP_CH time steps per warp keeps ~27 KB per warp in flight without holding registers.  Four independent
 // recurrences per lane give the instruction-level parallelism that the lower warp count takes away.  No
 // cross-warp synchronisation; per column the arithmetic (and its rounding order) is gae_segment's.
-constexpr int GP_CH = 8;                    // time steps per stage
-constexpr int GP_NS = 4;                    // ring depth
 constexpr int GP_COLS = 128;                // columns per warp (4 per lane)
-constexpr int GP_STAGE = GP_CH * (GP_COLS * 4 + GP_COLS * 4 + GP_COLS);
-constexpr int GP_WARPS = 2;
+int g_gae_variant = 0;                      // msat_tune("gae_variant", v): ring shape, see launch_gae
 
 __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem_dst)), "l"(gmem_src) : "memory");
@@ -140,6 +137,7 @@ __device__ __forceinline__ void gae_update(float r, float v, uint32_t dn, float 
     next_value = v;
 }
 
+template <int GP_CH, int GP_NS, int GP_WARPS>
 __global__ void __launch_bounds__(32 * GP_WARPS) gae_pipe_kernel(const float* __restrict__ reward, long long rs_t,
                                                                  const uint8_t* __restrict__ done,
                                                                  const float* __restrict__ value,
@@ -148,6 +146,7 @@ __global__ void __launch_bounds__(32 * GP_WARPS) gae_pipe_kernel(const float* __
                                                                  float* __restrict__ targets, int T, int B,
                                                                  double* __restrict__ stats) {
     extern __shared__ __align__(16) uint8_t gp_smem[];
+    constexpr int GP_STAGE = GP_CH * (GP_COLS * 4 + GP_COLS * 4 + GP_COLS);
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const int b = (blockIdx.x * GP_WARPS + w) * GP_COLS + 4 * lane;      // first of this lane's four columns
     if (b - 4 * lane >= B) return;                         // whole warp leaves
@@ -289,6 +288,28 @@ __global__ void __launch_bounds__(256) adv_normalize_kernel(float* __restrict__ 
     }
 }
 
+template <int CH, int NS, int WARPS>
+static cudaError_t launch_gae_pipe(const float* reward, long long rs_t, const uint8_t* done, const float* value,
+                                   const float* last_val, float gamma, float gl, float* adv, float* targets, int T, int B,
+                                   double* stats, cudaStream_t s) {
+    constexpr int kSmem = WARPS * NS * CH * (GP_COLS * 4 + GP_COLS * 4 + GP_COLS);
+    static_assert(kSmem <= 227 * 1024, "ring does not fit");
+    static std::atomic<unsigned long long> prepared{0};
+    int dev = 0;
+    cudaError_t err = cudaGetDevice(&dev);
+    if (err != cudaSuccess) return err;
+    if (!(prepared.load(std::memory_order_acquire) & (1ULL << (dev & 63)))) {
+        err = cudaFuncSetAttribute((const void*)gae_pipe_kernel<CH, NS, WARPS>,
+                                   cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem);
+        if (err != cudaSuccess) return err;
+        prepared.fetch_or(1ULL << (dev & 63), std::memory_order_release);
+    }
+    const int pgrid = (B + GP_COLS * WARPS - 1) / (GP_COLS * WARPS);
+    gae_pipe_kernel<CH, NS, WARPS><<<pgrid, 32 * WARPS, kSmem, s>>>(reward, rs_t, done, value, last_val, gamma, gl, adv,
+                                                                   targets, T, B, stats);
+    return cudaGetLastError();
+}
+
 cudaError_t launch_gae(const float* reward, long long rs_t, long long rs_b, const uint8_t* done, const float* value,
                        const float* last_val, float gamma, float gl, float* adv, float* targets, int T, int B,
                        double* stats, cudaStream_t s) {
@@ -305,20 +326,16 @@ cudaError_t launch_gae(const float* reward, long long rs_t, long long rs_b, cons
                           reinterpret_cast<uintptr_t>(targets)) & 15) == 0 &&
                         (reinterpret_cast<uintptr_t>(done) & 3) == 0;
     if (S == 1 && rows16 && !g_gae_force_plain) {
-        constexpr int kSmem = GP_WARPS * GP_NS * GP_STAGE;
-        static std::atomic<unsigned long long> prepared{0};
-        int dev = 0;
-        cudaError_t err = cudaGetDevice(&dev);
-        if (err != cudaSuccess) return err;
-        if (!(prepared.load(std::memory_order_acquire) & (1ULL << (dev & 63)))) {
-            err = cudaFuncSetAttribute((const void*)gae_pipe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem);
-            if (err != cudaSuccess) return err;
-            prepared.fetch_or(1ULL << (dev & 63), std::memory_order_release);
+        switch (g_gae_variant) {
+            case 1: return launch_gae_pipe<4, 6, 1>(reward, rs_t, done, value, last_val, gamma, gl, adv, targets, T, B, stats, s);
+            case 2: return launch_gae_pipe<4, 8, 1>(reward, rs_t, done, value, last_val, gamma, gl, adv, targets, T, B, stats, s);
+            case 3: return launch_gae_pipe<16, 3, 1>(reward, rs_t, done, value, last_val, gamma, gl, adv, targets, T, B, stats, s);
+            case 4: return launch_gae_pipe<8, 6, 1>(reward, rs_t, done, value, last_val, gamma, gl, adv, targets, T, B, stats, s);
+            case 5: return launch_gae_pipe<8, 3, 1>(reward, rs_t, done, value, last_val, gamma, gl, adv, targets, T, B, stats, s);
+            case 6: return launch_gae_pipe<4, 4, 1>(reward, rs_t, done, value, last_val, gamma, gl, adv, targets, T, B, stats, s);
+            case 7: return launch_gae_pipe<8, 4, 2>(reward, rs_t, done, value, last_val, gamma, gl, adv, targets, T, B, stats, s);
+            default: return launch_gae_pipe<8, 4, 1>(reward, rs_t, done, value, last_val, gamma, gl, adv, targets, T, B, stats, s);
         }
-        const int pgrid = (B + GP_COLS * GP_WARPS - 1) / (GP_COLS * GP_WARPS);
-        gae_pipe_kernel<<<pgrid, 32 * GP_WARPS, kSmem, s>>>(reward, rs_t, done, value, last_val, gamma, gl, adv, targets,
-                                                            T, B, stats);
-        return cudaGetLastError();
     }
 #define MSAT_GAE_LAUNCH(SS)                                                                                         \
     gae_kernel<SS><<<grid, 32 * SS, 0, s>>>(reward, rs_t, rs_b, done, value, last_val, gamma, gl, adv, targets, T, B, \

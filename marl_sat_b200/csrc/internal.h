@@ -30,8 +30,8 @@ inline GroupLayout group_layout(const Dims& d, bool obs) {
     o = (o + 7) & ~7;
     L.smx = o;  o += obs ? 8 * (d.fw + 2) : 0;    // {mask word, value word} per 32 observation ints
     L.bar = o;  o += 8;                           // mbarrier
-    L.misc = o; o += 16 + 64;                     // [0] #unsatisfied accumulator, [1] new problem idx, [2..3] reset key,
-                                                  // then float[16]: n_true / 3.0 table of the GNN clause features
+    L.misc = o; o += 16 + 128;                    // [0] #unsatisfied accumulator, [1] new problem idx, [2..3] reset key,
+                                                  // then float2[16]: {t > 0, t / 3.0} table of the GNN clause features
     L.total = (o + 127) & ~127;
     return L;
 }
@@ -100,6 +100,7 @@ struct EnvArgs {
 enum EnvMode { MODE_RESET = 0, MODE_STEP = 1, MODE_OBS = 2 };
 
 extern int g_gae_force_plain;   // gae.cu; msat_tune("gae_plain", 1)
+extern int g_gae_variant;       // gae.cu; msat_tune("gae_variant", v)
 
 struct ExportArgs {
     const uint8_t* bank;

@@ -105,34 +105,8 @@ __device__ __forceinline__ void build_truth_table(const Dims& d, const uint32_t*
     }
 }
 
-// Clause truth via warp ballots (env:130-156): lane = clause, ballot word = 32 clause-status bits,
-// __popc for the number of unsatisfied clauses.
-template <int GS>
-__device__ __forceinline__ void eval_clauses(const Dims& d, const uint16_t* lits, const uint8_t* tt, uint32_t* satw,
-                                             int* nunsat, int gt) {
-    const int lane = gt & 31;
-    int local = 0;
-    for (int w = gt >> 5; w < d.sw; w += GS / 32) {
-        const int c = w * 32 + lane;
-        const bool valid = c < d.m;
-        uint32_t cnt = 0u;
-        if (valid) {
-            if (d.k == 3) {
-                const uint32_t c0 = lits[c], c1 = lits[d.m + c], c2 = lits[2 * d.m + c];   // independent loads first
-                cnt = tt[c0] | tt[c1] | tt[c2];
-            } else {
-#pragma unroll 4
-                for (int j = 0; j < d.k; ++j) cnt |= tt[lits[lit_index(d.m, c, j)]];
-            }
-        }
-        const uint32_t word = __ballot_sync(0xffffffffu, cnt != 0u);
-        if (lane == 0) {
-            satw[w] = word;
-            if (nunsat) local += min(32, d.m - w * 32) - __popc(word);
-        }
-    }
-    if (nunsat && lane == 0 && local) atomicAdd(nunsat, local);
-}
+// Clause truth via warp ballots (env:130-156): lane = clause, ballot word = 32 clause-status bits, __popc for
+// the number of (un)satisfied clauses; the evaluators follow the bulk-store helpers below.
 
 // ---- bulk (TMA) store shared -> global ----------------------------------------------------------------
 __device__ __forceinline__ void tma_store_1d(void* gmem_dst, const void* smem_src, uint32_t bytes) {
@@ -149,47 +123,66 @@ __device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.b
 // learner:185 for every clause width.  The floats of up to kCfStageClauses clauses are staged in shared
 // memory (lane = clause, three conflict-free 4-byte stores) at the same 16-byte phase as their global
 // destination and leave as ONE bulk (TMA) store per pass; the <= 3 floats before / after the 16-byte
-// aligned body go out as scalars.  cf1[t] = t / 3.0 for t = 0..15.
+// aligned body go out as scalars.
 constexpr int kCfStageClauses = 256;
-template <int GS>
+
+// number of true literals of clause c (lane = clause); K3: three literals per clause, no loop
+template <bool K3>
+__device__ __forceinline__ uint32_t true_literals(const Dims& d, const uint16_t* lits, const uint8_t* tt, int c) {
+    if (K3) {
+        const uint32_t l0 = lits[c], l1 = lits[d.m + c], l2 = lits[2 * d.m + c];     // independent loads first
+        return (uint32_t)tt[l0] + tt[l1] + tt[l2];
+    }
+    uint32_t cnt = 0u;
+#pragma unroll 4
+    for (int j = 0; j < d.k; ++j) cnt += tt[lits[lit_index(d.m, c, j)]];
+    return cnt;
+}
+
+// cf01[t] = {t > 0 ? 1 : 0, t / 3.0} for t = 0..15: the first two clause features of a clause with t true literals
+template <int GS, bool K3>
 __device__ __forceinline__ void eval_clauses_gnn(const Dims& d, const uint16_t* lits, const uint8_t* tt, uint32_t* satw,
-                                                 int* nunsat, const float* cf1, uint8_t* stage,
+                                                 int* nunsat, const float2* cf01, uint8_t* stage,
                                                  float* __restrict__ cf_out, int gid, int gt) {
     const int lane = gt & 31;
-    int local = 0;
+    int nsat = 0;                                       // popc of the rounds this warp evaluates (warp-uniform)
     constexpr int kRoundsPerPass = kCfStageClauses / 32;
+    const int full = d.m >> 5;                          // rounds in which every lane has a clause
     for (int w0 = 0; w0 < d.sw; w0 += kRoundsPerPass) {
         const int c0 = w0 * 32;
         const int c1 = min(d.m, c0 + kCfStageClauses);
         uint8_t* gdst = reinterpret_cast<uint8_t*>(cf_out + 3 * (size_t)c0);
         const uint32_t phase16 = (uint32_t)(reinterpret_cast<uintptr_t>(gdst) & 15u);
-        float* sf = reinterpret_cast<float*>(stage + phase16);
         if (w0 > 0) {
             if (gt == 0) tma_store_wait_read();        // the previous pass has left the staging buffer
             group_sync<GS>(gid);
         }
-        for (int w = w0 + (gt >> 5); w < min(d.sw, w0 + kRoundsPerPass); w += GS / 32) {
+        const int wend = min(d.sw, w0 + kRoundsPerPass);
+        float* o = reinterpret_cast<float*>(stage + phase16) + 3 * (32 * (gt >> 5) + lane);
+        int w = w0 + (gt >> 5);
+        for (; w < min(wend, full); w += GS / 32, o += 3 * GS) {
+            const uint32_t cnt = true_literals<K3>(d, lits, tt, w * 32 + lane);
+            const float2 f = cf01[cnt];
+            o[0] = f.x;
+            o[1] = f.y;
+            o[2] = 1.0f;
+            const uint32_t word = __ballot_sync(0xffffffffu, cnt != 0u);
+            nsat += __popc(word);
+            if (lane == 0) satw[w] = word;
+        }
+        if (w < wend) {                                 // the ragged last round (w == full)
             const int c = w * 32 + lane;
-            const bool valid = c < d.m;
             uint32_t cnt = 0u;
-            if (valid) {
-                if (d.k == 3) {
-                    const uint32_t l0 = lits[c], l1 = lits[d.m + c], l2 = lits[2 * d.m + c];
-                    cnt = (uint32_t)tt[l0] + tt[l1] + tt[l2];
-                } else {
-#pragma unroll 4
-                    for (int j = 0; j < d.k; ++j) cnt += tt[lits[lit_index(d.m, c, j)]];
-                }
-                float* o = sf + 3 * (c - c0);
-                o[0] = cnt ? 1.0f : 0.0f;
-                o[1] = cnt < 16u ? cf1[cnt] : __fdiv_rn((float)cnt, 3.0f);
+            if (c < d.m) {
+                cnt = true_literals<K3>(d, lits, tt, c);
+                const float2 f = cf01[cnt];
+                o[0] = f.x;
+                o[1] = f.y;
                 o[2] = 1.0f;
             }
             const uint32_t word = __ballot_sync(0xffffffffu, cnt != 0u);
-            if (lane == 0) {
-                satw[w] = word;
-                local += min(32, d.m - w * 32) - __popc(word);
-            }
+            nsat += __popc(word);
+            if (lane == 0) satw[w] = word;
         }
         fence_proxy_async();                           // staged floats -> visible to the bulk-copy engine
         group_sync<GS>(gid);
@@ -207,7 +200,28 @@ __device__ __forceinline__ void eval_clauses_gnn(const Dims& d, const uint16_t* 
             if (mine) *reinterpret_cast<float*>(gdst + i) = *reinterpret_cast<const float*>(stage + phase16 + i);
         }
     }
-    if (lane == 0 && local) atomicAdd(nunsat, local);
+    // every lane of a warp holds the same count; one-warp groups need no shared accumulator
+    if (GS == 32) *nunsat = d.m - nsat;
+    else if (lane == 0 && nsat) atomicAdd(nunsat, -nsat);
+}
+
+// Plain evaluation (no clause features): status bits + number of unsatisfied clauses (optional).
+template <int GS, bool K3>
+__device__ __forceinline__ void eval_clauses(const Dims& d, const uint16_t* lits, const uint8_t* tt, uint32_t* satw,
+                                             int* nunsat, int gt) {
+    const int lane = gt & 31;
+    int nsat = 0;
+    for (int w = gt >> 5; w < d.sw; w += GS / 32) {
+        const int c = w * 32 + lane;
+        const uint32_t cnt = c < d.m ? true_literals<K3>(d, lits, tt, c) : 0u;
+        const uint32_t word = __ballot_sync(0xffffffffu, cnt != 0u);
+        nsat += __popc(word);
+        if (lane == 0) satw[w] = word;
+    }
+    if (nunsat) {
+        if (GS == 32) *nunsat = d.m - nsat;
+        else if (lane == 0 && nsat) atomicAdd(nunsat, -nsat);
+    }
 }
 
 // assign = randint(key, (n,), 0, 2) (env:162): bit 0 of threefry_2x32(split(key)[1], arange(n)).
@@ -433,7 +447,7 @@ __global__ void __launch_bounds__(kCtaThreads, (MULTI || !OBS) ? 4 : 8) env_kern
     uint32_t* st_tail = st + d.aw;
     const uint32_t tma_bytes = OBS ? (uint32_t)d.rec_bytes : (uint32_t)d.lits_bytes;
     const bool want_cf = !OBS && a.gnn_cf != nullptr;
-    float* cf1 = reinterpret_cast<float*>(misc + 4);     // n_true / 3.0 for n_true = 0..15 (learner:185)
+    float2* cf01 = reinterpret_cast<float2*>(misc + 4);  // {t > 0, t / 3.0} for t = 0..15 true literals (learner:185)
 
     // ---- stage the state record (plain loads) ----
     if (MODE == MODE_RESET) {
@@ -443,10 +457,10 @@ __global__ void __launch_bounds__(kCtaThreads, (MULTI || !OBS) ? 4 : 8) env_kern
         for (int i = gt; i < d.state_words; i += GS) st[i] = sin[i];
     }
     if (gt == 0) {
-        misc[0] = 0;
+        misc[0] = d.m;              // #unsatisfied accumulator of multi-warp groups: m minus the satisfied counts
         mbar_init(bar, 1);
     }
-    if (want_cf && gt < 16) cf1[gt] = __fdiv_rn((float)gt, 3.0f);
+    if (want_cf && gt < 16) cf01[gt] = make_float2(gt > 0 ? 1.0f : 0.0f, __fdiv_rn((float)gt, 3.0f));
     group_sync<GS>(gid);
 
     // Every thread keeps its own copy of the scalar state fields in registers from here on: thread 0 rewrites
@@ -484,7 +498,8 @@ __global__ void __launch_bounds__(kCtaThreads, (MULTI || !OBS) ? 4 : 8) env_kern
             }
             build_truth_table<GS>(d, st, tt, gt);
             group_sync<GS>(gid);
-            eval_clauses<GS>(d, lits, tt, satw_old, nullptr, gt);
+            if (d.k == 3) eval_clauses<GS, true>(d, lits, tt, satw_old, nullptr, gt);
+            else eval_clauses<GS, false>(d, lits, tt, satw_old, nullptr, gt);
             group_sync<GS>(gid);
         }
 
@@ -504,8 +519,13 @@ __global__ void __launch_bounds__(kCtaThreads, (MULTI || !OBS) ? 4 : 8) env_kern
         group_sync<GS>(gid);
 
         float* cf_row = (want_cf && emit) ? a.gnn_cf + row * d.m * 3 : nullptr;
-        if (cf_row) eval_clauses_gnn<GS>(d, lits, tt, satw, &misc[0], cf1, stage, cf_row, gid, gt);
-        else eval_clauses<GS>(d, lits, tt, satw, &misc[0], gt);
+        if (cf_row) {
+            if (d.k == 3) eval_clauses_gnn<GS, true>(d, lits, tt, satw, &misc[0], cf01, stage, cf_row, gid, gt);
+            else eval_clauses_gnn<GS, false>(d, lits, tt, satw, &misc[0], cf01, stage, cf_row, gid, gt);
+        } else {
+            if (d.k == 3) eval_clauses<GS, true>(d, lits, tt, satw, &misc[0], gt);
+            else eval_clauses<GS, false>(d, lits, tt, satw, &misc[0], gt);
+        }
         group_sync<GS>(gid);
         nunsat = misc[0];
 
@@ -567,7 +587,7 @@ __global__ void __launch_bounds__(kCtaThreads, (MULTI || !OBS) ? 4 : 8) env_kern
                 }
                 pidx = pidx < 0 ? 0 : (pidx >= a.P ? a.P - 1 : pidx);
                 if (gt == 0) {
-                    misc[0] = 0;
+                    misc[0] = d.m;
                     if (a.reset_count) atomicAdd(a.reset_count, 1ULL);
                     if (pidx != loaded_pidx) {
                         fence_proxy_async();
@@ -591,9 +611,11 @@ __global__ void __launch_bounds__(kCtaThreads, (MULTI || !OBS) ? 4 : 8) env_kern
                 if (cf_row) {
                     if (gt == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
                     group_sync<GS>(gid);
-                    eval_clauses_gnn<GS>(d, lits, tt, satw, &misc[0], cf1, stage, cf_row, gid, gt);
+                    if (d.k == 3) eval_clauses_gnn<GS, true>(d, lits, tt, satw, &misc[0], cf01, stage, cf_row, gid, gt);
+                    else eval_clauses_gnn<GS, false>(d, lits, tt, satw, &misc[0], cf01, stage, cf_row, gid, gt);
                 } else {
-                    eval_clauses<GS>(d, lits, tt, satw, &misc[0], gt);
+                    if (d.k == 3) eval_clauses<GS, true>(d, lits, tt, satw, &misc[0], gt);
+                    else eval_clauses<GS, false>(d, lits, tt, satw, &misc[0], gt);
                 }
                 group_sync<GS>(gid);
                 nunsat = misc[0];
@@ -612,7 +634,7 @@ __global__ void __launch_bounds__(kCtaThreads, (MULTI || !OBS) ? 4 : 8) env_kern
         if (!last) {
             if (cf_row && gt == 0) tma_store_wait_read();   // the staging buffer is rewritten by the next step
             group_sync<GS>(gid);           // every lane has read misc[0] / the state of this step
-            if (gt == 0) misc[0] = 0;      // published by the barrier after the next step's flips
+            if (gt == 0) misc[0] = d.m;    // published by the barrier after the next step's flips
         }
     }
 
