@@ -75,6 +75,31 @@ def advantage_stats(adv: torch.Tensor, stats: Optional[torch.Tensor] = None) -> 
     return stats
 
 
+def _world_size(group=None) -> int:
+    if torch.distributed.is_available() and torch.distributed.is_initialized():
+        return torch.distributed.get_world_size(group)
+    return 1
+
+
+def allreduce_stats(stats: torch.Tensor, group=None) -> torch.Tensor:
+    """Sum a rank-local float64 statistics vector -- (count, sum, sum of squares) of the advantages, or the
+    five rollout-metric sums -- over all ranks.  Returns a private reduced copy (the caller's local values
+    stay local); the input itself when ``torch.distributed`` is not initialised or has one rank.  Works for
+    CPU (gloo) and CUDA (nccl) tensors: this is the only collective of the advantage path."""
+    if _world_size(group) <= 1:
+        return stats
+    out = stats.clone()
+    torch.distributed.all_reduce(out, op=torch.distributed.ReduceOp.SUM, group=group)
+    return out
+
+
+def mean_std_from_stats(stats: torch.Tensor):
+    """``(mean, population std)`` from (count, sum, sum of squares), in float64 like ``adv_normalize_kernel``."""
+    n, s, ss = (float(x) for x in stats.tolist())
+    mean = s / n
+    return mean, max(ss / n - mean * mean, 0.0) ** 0.5
+
+
 def normalize_advantages(adv: torch.Tensor, stats: Optional[torch.Tensor] = None, group=None) -> torch.Tensor:
     """In place ``adv = (adv - mean) / (std + 1e-8)`` with the global population std (learner:530-532).
     ``stats``: the local (count, sum, sum of squares) if ``calculate_gae`` already produced them (saves a
@@ -83,14 +108,9 @@ def normalize_advantages(adv: torch.Tensor, stats: Optional[torch.Tensor] = None
     if stats is not None and (stats.dtype != torch.float64 or stats.numel() != 3):
         raise ValueError("stats must be float64[3]")
     work = adv if adv.is_contiguous() else adv.contiguous()      # a strided view is normalised through a copy ...
-    distributed = torch.distributed.is_available() and torch.distributed.is_initialized() and \
-        torch.distributed.get_world_size(group) > 1
     if stats is None:
         stats = advantage_stats(work)
-    elif distributed:
-        stats = stats.clone()                                    # the caller's local statistics stay local
-    if distributed:
-        torch.distributed.all_reduce(stats, op=torch.distributed.ReduceOp.SUM, group=group)
+    stats = allreduce_stats(stats, group)                         # global (count, sum, sum of squares)
     _lib.check(lib.msat_adv_normalize(_ptr(work), work.numel(), _ptr(stats), _stream_ptr(work.device)),
                "msat_adv_normalize")
     if work is not adv:

@@ -26,17 +26,23 @@ def rollout_metric_sums(reward: torch.Tensor, done: torch.Tensor, solved: torch.
     return sums
 
 
-def rollout_metrics(reward, done, solved, num_unsatisfied, episode_step, num_envs_global=None, group=None) -> Dict[str, float]:
-    """``mean_episodic_return``, ``solve_rate``, ``avg_unsatisfied_clauses``, ``avg_steps_to_solve``
-    (learner:664-686).  ``reward`` is ``[T,B,A]`` (agent 0 read) or ``[T,B]``."""
-    sums = rollout_metric_sums(reward, done, solved, num_unsatisfied, episode_step)
-    B = done.shape[1]
-    if torch.distributed.is_available() and torch.distributed.is_initialized() and \
-            torch.distributed.get_world_size(group) > 1:
-        torch.distributed.all_reduce(sums, group=group)
-        B = num_envs_global if num_envs_global is not None else B * torch.distributed.get_world_size(group)
-    total_reward, finished, n_solved, unsat, steps = sums.tolist()
-    return {"mean_episodic_return": total_reward / B,                      # learner:666-668
+def metrics_from_sums(sums, num_envs_global: int) -> Dict[str, float]:
+    """learner:664-686 from the five (global) sums."""
+    total_reward, finished, n_solved, unsat, steps = (float(x) for x in sums.tolist())
+    return {"mean_episodic_return": total_reward / num_envs_global,         # learner:666-668
             "solve_rate": n_solved / max(finished, 1.0),                   # learner:674
             "avg_unsatisfied_clauses": unsat / max(finished, 1.0),         # learner:680
             "avg_steps_to_solve": steps / max(n_solved, 1.0)}              # learner:686
+
+
+def rollout_metrics(reward, done, solved, num_unsatisfied, episode_step, num_envs_global=None, group=None) -> Dict[str, float]:
+    """``mean_episodic_return``, ``solve_rate``, ``avg_unsatisfied_clauses``, ``avg_steps_to_solve``
+    (learner:664-686).  ``reward`` is ``[T,B,A]`` (agent 0 read) or ``[T,B]``.  With ``torch.distributed``
+    initialised the five sums are all-reduced, so every rank reports the metrics of the global batch."""
+    from .gae import _world_size, allreduce_stats
+    sums = allreduce_stats(rollout_metric_sums(reward, done, solved, num_unsatisfied, episode_step), group)
+    B = done.shape[1]
+    world = _world_size(group)
+    if world > 1:
+        B = num_envs_global if num_envs_global is not None else B * world
+    return metrics_from_sums(sums, B)

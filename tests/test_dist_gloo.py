@@ -1,7 +1,9 @@
 """world_size-2 tests on CPU (gloo) of the multi-rank host logic: contiguous env sharding, the
 shard-invariant per-env key derivation (checked with the oracle's PRNG on each rank's slice) and the
-(count, sum, sum-of-squares) all-reduce that makes the advantage normalisation global
-(learner:530-532).  The CUDA kernels themselves are exercised on the GPU box."""
+product's own collectives -- ``allreduce_stats`` / ``mean_std_from_stats`` / ``metrics_from_sums``, the
+functions ``normalize_advantages`` and ``rollout_metrics`` call (learner:530-532, 661-686; SURVEY.md section
+8e).  The kernels around them run in tests/test_dist_gpu.py (two ranks on one GPU) and in bench.py's
+multi-GPU self-check."""
 import os
 import socket
 
@@ -35,13 +37,27 @@ def _worker(rank, world, port, Bg, P, T, q):
         rng = np.random.default_rng(3)
         adv_global = rng.standard_normal((T, Bg)).astype(np.float32)
         adv = adv_global[:, off:off + cnt]
-        stats = torch.tensor([adv.size, adv.astype(np.float64).sum(), (adv.astype(np.float64) ** 2).sum()],
+        local = torch.tensor([adv.size, adv.astype(np.float64).sum(), (adv.astype(np.float64) ** 2).sum()],
                              dtype=torch.float64)
-        dist.all_reduce(stats, op=dist.ReduceOp.SUM)
-        n, s, ss = stats.tolist()
-        mean = s / n
-        std = max(ss / n - mean * mean, 0.0) ** 0.5
+        # the product's own collective + finalisation (what normalize_advantages / rollout_metrics call)
+        stats = M.allreduce_stats(local)
+        assert stats is not local and float(local[0]) == adv.size          # the local statistics stay local
+        mean, std = M.mean_std_from_stats(stats)
         norm = (adv - np.float32(mean)) / (np.float32(std) + np.float32(1e-8))
+        # rollout-metric sums: this rank's share of {reward, finished, solved, unsat at finish, steps of solved}
+        done = rng.random((T, Bg)) < 0.3
+        solved = done & (rng.random((T, Bg)) < 0.5)
+        nunsat = rng.integers(0, 9, size=(T, Bg))
+        estep = rng.integers(1, 50, size=(T, Bg))
+        sl = np.s_[:, off:off + cnt]
+        sums = torch.tensor([solved[sl].sum(), done[sl].sum(), (solved & done)[sl].sum(), (nunsat * done)[sl].sum(),
+                             (estep * (solved & done))[sl].sum()], dtype=torch.float64)
+        met = M.metrics_from_sums(M.allreduce_stats(sums), Bg)
+        exp = {"mean_episodic_return": solved.sum() / Bg, "solve_rate": (solved & done).sum() / max(done.sum(), 1),
+               "avg_unsatisfied_clauses": (nunsat * done).sum() / max(done.sum(), 1),
+               "avg_steps_to_solve": (estep * (solved & done)).sum() / max((solved & done).sum(), 1)}
+        for k_, v in exp.items():
+            assert abs(met[k_] - float(v)) < 1e-9, (k_, met[k_], v)
         gathered = [None] * world
         dist.all_gather_object(gathered, (off, cnt, idx, keys, norm))
         if rank == 0:
