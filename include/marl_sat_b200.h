@@ -243,6 +243,19 @@ int msat_host_wait(msat_host_pipe* pipe, int32_t slot);
 /* Releases the library's internal per-device streams / events (msat_rollout_step_host). */
 int msat_shutdown(void);
 
+/* Clause-satisfaction update of the step launches that write NO observations (msat_rollout_step_gnn,
+ * msat_step / msat_rollout_step(s) with obs == NULL).  Call before compiling a bank or allocating state:
+ * rec_bytes and state_words change with the mode (re-read them with msat_plan_dims).
+ *   MSAT_CLAUSES_FULL (default)   every step re-evaluates all m clauses from the staged literal block;
+ *   MSAT_CLAUSES_INCREMENTAL      the state carries a 4-bit true-literal count per clause and the bank
+ *        record the var -> clause occurrence lists (CSR); a step touches only the clauses adjacent to the
+ *        flipped variables (env:130-156 restricted to those clauses) and never reads the literal block unless
+ *        the episode restarts.  Needs lits_per_clause <= 15.  Results are bit-identical in both modes;
+ *        launches that do write observations keep the counts up to date with a full evaluation. */
+#define MSAT_CLAUSES_FULL        0
+#define MSAT_CLAUSES_INCREMENTAL 1
+int msat_plan_set_clause_update(msat_plan* plan, int32_t mode);
+
 /* Diagnostics: while `counter_dev` (a device uint64, 8-byte aligned, owned by the caller) is set, every
  * auto-reset performed by a step launch that uses this plan adds 1 to it.  NULL switches it off. */
 int msat_plan_set_reset_counter(msat_plan* plan, uint64_t* counter_dev);

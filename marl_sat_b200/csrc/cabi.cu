@@ -101,6 +101,53 @@ inline void fill_reward(EnvArgs& a, const msat_plan* plan, int32_t* newly) {
     a.reset_count = plan->reset_counter;
 }
 
+// Sizes that depend on the clause-update mode (d.cnt_words), group sizes and shared-memory layouts.
+int finish_plan(msat_plan* p) {
+    Dims& d = p->d;
+    const int n = d.n, m = d.m, k = d.k;
+    d.rec_copy_bytes = (d.lits_bytes + 4 * (d.fw + 1) + 15) & ~15;
+    if (d.cnt_words) {
+        // incremental clause update: var -> clause occurrence lists (CSR) behind the mask stream --
+        // u16 row_off[n + 1] (padded to 8 entries), u16 occ[m * k] = (clause << 1) | negated
+        d.csr_off = d.rec_copy_bytes;
+        d.rec_bytes = (d.csr_off + 2 * ((n + 1 + 7) & ~7) + 2 * m * k + 127) & ~127;
+    } else {
+        d.csr_off = 0;
+        d.rec_bytes = (d.rec_copy_bytes + 127) & ~127;
+    }
+    d.state_words = (d.aw + 4 + d.cnt_words + 3) & ~3;
+
+    const int chunks = (d.AD + 3) / 4;
+    int gs = p->requested_group_threads;
+    // measured on B200 (profiles/r1_group_size_sweep.md): about 16-24 store iterations per thread is the sweet
+    // spot -- larger groups idle most lanes in the short per-env phases, smaller ones serialise the stores
+    if (gs == 0) gs = chunks <= 768 ? 32 : (chunks <= 1536 ? 64 : (chunks <= 3072 ? 128 : 256));
+    if (gs != 32 && gs != 64 && gs != 128 && gs != 256) return MSAT_EINVAL;
+    const GroupLayout L = group_layout(d, true);
+    const int kChain = 40 * kMaxFusedSteps;      // room for the K key chains of a multi-step launch
+    // grow the group until one CTA's groups fit in shared memory
+    while (gs < 256 && (long long)L.total * (kCtaThreads / gs) + kChain > kMaxSmem) gs *= 2;
+    if ((long long)L.total * (kCtaThreads / gs) + kChain > kMaxSmem) return MSAT_EUNSUPPORTED;
+    p->group_threads = gs;
+    p->layout_obs = L;
+    p->layout_noobs = group_layout(d, false);
+    p->group_smem_bytes = L.total;
+    p->smem_bytes = L.total * (kCtaThreads / gs);
+    // launches that write no observations (emit_obs off, GNN-input mode) have ~m clause evaluations of work per
+    // env and stage only the literal block: one warp per env unless the caller pinned the group size or eight
+    // groups do not fit in shared memory
+    const GroupLayout Ln = p->layout_noobs;
+    int gn = p->requested_group_threads ? gs : 32;
+    while (gn < 256 && (long long)Ln.total * (kCtaThreads / gn) + kChain > kMaxSmem) gn *= 2;
+    if ((long long)Ln.total * (kCtaThreads / gn) + kChain > kMaxSmem) return MSAT_EUNSUPPORTED;
+    p->group_threads_noobs = gn;
+    p->smem_bytes_noobs = Ln.total * (kCtaThreads / gn);
+    p->compile_smem_bytes = 4 * (m + n) * d.agw + (d.cnt_words ? 4 * (n + 1) : 0);
+    if (p->compile_smem_bytes > kMaxSmem) return MSAT_EUNSUPPORTED;
+    (void)k;
+    return MSAT_OK;
+}
+
 }  // namespace
 
 extern "C" {
@@ -141,35 +188,9 @@ int msat_plan_create(msat_plan** out, int32_t n, int32_t m, int32_t k, int32_t A
     d.agw = (A + 31) / 32;
     d.inv_D = (uint32_t)(((1ULL << 32) + (uint64_t)d.D - 1) / (uint64_t)d.D);
     d.lits_bytes = (m * k * 2 + 15) & ~15;
-    d.rec_bytes = (d.lits_bytes + 4 * (d.fw + 1) + 127) & ~127;
-    d.state_words = (d.aw + 4 + 3) & ~3;
-
-    const int chunks = (d.AD + 3) / 4;
-    int gs = group_threads;
-    // measured on B200 (profiles/r1_group_size_sweep.md): about 16-24 store iterations per thread is the sweet
-    // spot -- larger groups idle most lanes in the short per-env phases, smaller ones serialise the stores
-    if (gs == 0) gs = chunks <= 768 ? 32 : (chunks <= 1536 ? 64 : (chunks <= 3072 ? 128 : 256));
-    if (gs != 32 && gs != 64 && gs != 128 && gs != 256) { delete p; return MSAT_EINVAL; }
-    const GroupLayout L = group_layout(d, true);
-    const int kChain = 40 * kMaxFusedSteps;      // room for the K key chains of a multi-step launch
-    // grow the group until one CTA's groups fit in shared memory
-    while (gs < 256 && (long long)L.total * (kCtaThreads / gs) + kChain > kMaxSmem) gs *= 2;
-    if ((long long)L.total * (kCtaThreads / gs) + kChain > kMaxSmem) { delete p; return MSAT_EUNSUPPORTED; }
-    p->group_threads = gs;
-    p->layout_obs = L;
-    p->layout_noobs = group_layout(d, false);
-    p->group_smem_bytes = L.total;
-    p->smem_bytes = L.total * (kCtaThreads / gs);
-    // launches that write no observations (emit_obs off, GNN-input mode) have ~m clause evaluations of work per
-    // env and stage only the literal block: one warp per env unless the caller pinned the group size or eight
-    // groups do not fit in shared memory
-    const GroupLayout Ln = group_layout(d, false);
-    int gn = group_threads ? gs : 32;
-    while (gn < 256 && (long long)Ln.total * (kCtaThreads / gn) + kChain > kMaxSmem) gn *= 2;
-    p->group_threads_noobs = gn;
-    p->smem_bytes_noobs = Ln.total * (kCtaThreads / gn);
-    p->compile_smem_bytes = 4 * (m + n) * d.agw;
-    if (p->compile_smem_bytes > kMaxSmem) { delete p; return MSAT_EUNSUPPORTED; }
+    p->requested_group_threads = group_threads;
+    const int rc = finish_plan(p);
+    if (rc != MSAT_OK) { delete p; return rc; }
     *out = p;
     return MSAT_OK;
 }
@@ -183,6 +204,19 @@ int msat_plan_set_reward(msat_plan* plan, int32_t mode, double gamma, double r_c
     plan->r_clause = (float)r_clause;
     plan->r_sat = (float)r_sat;
     return MSAT_OK;
+}
+
+int msat_plan_set_clause_update(msat_plan* plan, int32_t mode) {
+    if (!plan || (mode != MSAT_CLAUSES_FULL && mode != MSAT_CLAUSES_INCREMENTAL)) return MSAT_EINVAL;
+    if (mode == MSAT_CLAUSES_INCREMENTAL && plan->d.k > 15) return MSAT_EUNSUPPORTED;     // 4-bit counts
+    const int old = plan->d.cnt_words;
+    plan->d.cnt_words = mode == MSAT_CLAUSES_INCREMENTAL ? (plan->d.m + 7) / 8 : 0;
+    const int rc = finish_plan(plan);
+    if (rc != MSAT_OK) {
+        plan->d.cnt_words = old;
+        finish_plan(plan);
+    }
+    return rc;
 }
 
 int msat_plan_set_reset_counter(msat_plan* plan, uint64_t* counter_dev) {

@@ -12,7 +12,11 @@ struct Dims {
     int base, rem;        // contiguous balanced grouping: size_a = base + (a < rem)
     int aw, sw, xw, fw;   // words: assignment, clause status, obs value vector (+1 pad), flat mask stream
     int lits_bytes;       // padded byte size of the literal-code block inside a bank record
-    int rec_bytes;        // bank record size (multiple of 128)
+    int rec_bytes;        // bank record size = stride between records (multiple of 128)
+    int rec_copy_bytes;   // leading part staged by observation-writing launches: literals + agent-mask stream
+    int csr_off;          // byte offset of the var -> clause occurrence lists inside a record (0 = not built)
+    int cnt_words;        // incremental clause update: words of per-clause true-literal counts (4 bits each) in the
+                          // state record after the 4 scalar fields; 0 = full recompute (default)
     int state_words;      // env-state record words (multiple of 4)
     int agw;              // words of an agent bit-set = ceil(A/32)
     uint32_t inv_D;       // ceil(2^32 / D): j / D = umulhi(j, inv_D) (minus 1 when that overshoots)

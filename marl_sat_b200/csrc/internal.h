@@ -20,7 +20,7 @@ constexpr int kCfStageBytes = 12 * 256 + 16;      // clause-feature staging of e
 inline GroupLayout group_layout(const Dims& d, bool obs) {
     GroupLayout L;
     int o = 0;
-    L.rec = o;  o += obs ? d.rec_bytes : ((d.lits_bytes + 127) & ~127);   // TMA destination, 128-byte aligned
+    L.rec = o;  o += ((obs ? d.rec_copy_bytes : d.lits_bytes) + 127) & ~127;   // TMA destination, 128-byte aligned
     L.st = o;   o += 4 * d.state_words;           // state record (multiple of 16 bytes)
     L.stage = o; o += obs ? 0 : kCfStageBytes;    // 16-byte aligned (rec and state sizes are multiples of 16)
     L.satw = o; o += 4 * d.sw;
@@ -47,6 +47,7 @@ struct msat_plan {
     int smem_bytes_noobs;
     msat::GroupLayout layout_obs, layout_noobs;   // shared-memory carve-up of one env group, computed once
     int compile_smem_bytes;
+    int requested_group_threads = 0;
     int reward_mode = 0;       // MSAT_REWARD_SPARSE / MSAT_REWARD_SHAPED (msat_plan_set_reward)
     float r_gamma = 0.99f, r_clause = 0.02f, r_sat = 1.0f;
     unsigned long long* reset_counter = nullptr;   // device counter of auto-resets (diagnostics), or null

@@ -82,6 +82,40 @@ __global__ void __launch_bounds__(256) compile_bank_kernel(Dims d, const int32_t
         }
         mflat[w] = bits;
     }
+    if (d.cnt_words) {
+        // var -> clause occurrence lists for the incremental clause update: row_off[v] .. row_off[v+1] index
+        // occ[], an entry is (clause << 1) | negated; rows are filled in clause-major literal order
+        int* cnt = reinterpret_cast<int*>(csm + (d.m + d.n) * d.agw);      // [n + 1]
+        uint16_t* row_off = reinterpret_cast<uint16_t*>(rec + d.csr_off);
+        uint16_t* occ = row_off + ((d.n + 1 + 7) & ~7);
+        __syncthreads();
+        for (int i = tid; i <= d.n; i += nt) cnt[i] = 0;
+        __syncthreads();
+        for (int i = tid; i < d.m * d.k; i += nt) {
+            const uint32_t code = lits[lit_index(d.m, i / d.k, i % d.k)];
+            if (code != lit_pad(d)) atomicAdd(&cnt[code >> 1], 1);
+        }
+        __syncthreads();
+        if (tid == 0) {
+            int run = 0;
+            for (int v = 0; v < d.n; ++v) {
+                const int c = cnt[v];
+                cnt[v] = run;
+                row_off[v] = (uint16_t)run;
+                run += c;
+            }
+            row_off[d.n] = (uint16_t)run;
+        }
+        __syncthreads();
+        for (int v = tid; v < d.n; v += nt) {
+            int o = cnt[v];
+            for (int i = 0; i < d.m * d.k; ++i) {
+                const int c = i / d.k;
+                const uint32_t code = lits[lit_index(d.m, c, i - c * d.k)];
+                if (code != lit_pad(d) && (int)(code >> 1) == v) occ[o++] = (uint16_t)((c << 1) | (code & 1u));
+            }
+        }
+    }
 }
 
 // =====================================================================================
@@ -140,9 +174,21 @@ __device__ __forceinline__ uint32_t true_literals(const Dims& d, const uint16_t*
 }
 
 // cf01[t] = {t > 0 ? 1 : 0, t / 3.0} for t = 0..15: the first two clause features of a clause with t true literals
-template <int GS, bool K3>
-__device__ __forceinline__ void eval_clauses_gnn(const Dims& d, const uint16_t* lits, const uint8_t* tt, uint32_t* satw,
-                                                 int* nunsat, const float2* cf01, uint8_t* stage,
+// True-literal count of clause c for the evaluators below.  INCR: the 4-bit count carried in the state (kept
+// up to date by apply_actions_incr); otherwise from the staged literals, optionally packed into `cnt_store`
+// (zeroed by the caller) so that a state of an incremental plan leaves every kernel with valid counts.
+template <bool K3, bool INCR>
+__device__ __forceinline__ uint32_t clause_count(const Dims& d, const uint16_t* lits, const uint8_t* tt,
+                                                 uint32_t* cntw, int c) {
+    if (INCR) return (cntw[c >> 3] >> (4 * (c & 7))) & 15u;
+    const uint32_t cnt = true_literals<K3>(d, lits, tt, c);
+    if (cntw && cnt) atomicOr(&cntw[c >> 3], cnt << (4 * (c & 7)));
+    return cnt;
+}
+
+template <int GS, bool K3, bool INCR>
+__device__ __forceinline__ void eval_clauses_gnn(const Dims& d, const uint16_t* lits, const uint8_t* tt, uint32_t* cntw,
+                                                 uint32_t* satw, int* nunsat, const float2* cf01, uint8_t* stage,
                                                  float* __restrict__ cf_out, int gid, int gt) {
     const int lane = gt & 31;
     int nsat = 0;                                       // popc of the rounds this warp evaluates (warp-uniform)
@@ -161,7 +207,7 @@ __device__ __forceinline__ void eval_clauses_gnn(const Dims& d, const uint16_t* 
         float* o = reinterpret_cast<float*>(stage + phase16) + 3 * (32 * (gt >> 5) + lane);
         int w = w0 + (gt >> 5);
         for (; w < min(wend, full); w += GS / 32, o += 3 * GS) {
-            const uint32_t cnt = true_literals<K3>(d, lits, tt, w * 32 + lane);
+            const uint32_t cnt = clause_count<K3, INCR>(d, lits, tt, cntw, w * 32 + lane);
             const float2 f = cf01[cnt];
             o[0] = f.x;
             o[1] = f.y;
@@ -174,7 +220,7 @@ __device__ __forceinline__ void eval_clauses_gnn(const Dims& d, const uint16_t* 
             const int c = w * 32 + lane;
             uint32_t cnt = 0u;
             if (c < d.m) {
-                cnt = true_literals<K3>(d, lits, tt, c);
+                cnt = clause_count<K3, INCR>(d, lits, tt, cntw, c);
                 const float2 f = cf01[cnt];
                 o[0] = f.x;
                 o[1] = f.y;
@@ -206,14 +252,14 @@ __device__ __forceinline__ void eval_clauses_gnn(const Dims& d, const uint16_t* 
 }
 
 // Plain evaluation (no clause features): status bits + number of unsatisfied clauses (optional).
-template <int GS, bool K3>
-__device__ __forceinline__ void eval_clauses(const Dims& d, const uint16_t* lits, const uint8_t* tt, uint32_t* satw,
-                                             int* nunsat, int gt) {
+template <int GS, bool K3, bool INCR>
+__device__ __forceinline__ void eval_clauses(const Dims& d, const uint16_t* lits, const uint8_t* tt, uint32_t* cntw,
+                                             uint32_t* satw, int* nunsat, int gt) {
     const int lane = gt & 31;
     int nsat = 0;
     for (int w = gt >> 5; w < d.sw; w += GS / 32) {
         const int c = w * 32 + lane;
-        const uint32_t cnt = c < d.m ? true_literals<K3>(d, lits, tt, c) : 0u;
+        const uint32_t cnt = c < d.m ? clause_count<K3, INCR>(d, lits, tt, cntw, c) : 0u;
         const uint32_t word = __ballot_sync(0xffffffffu, cnt != 0u);
         nsat += __popc(word);
         if (lane == 0) satw[w] = word;
@@ -265,6 +311,54 @@ __device__ __forceinline__ void apply_actions(const Dims& d, const int32_t* __re
                 const int v = group_start(d, a) + j;
                 atomicXor(&assign[v >> 5], 1u << (v & 31));
             }
+        }
+    }
+}
+
+// Incremental clause update (env:130-156 restricted to the clauses adjacent to the flipped variables): every
+// flipping (agent, variable) walks the variable's occurrence list in the bank record (global memory, read
+// once) and moves the 4-bit true-literal count of each adjacent clause by +-1.  A variable flips at most
+// once per step (agents own disjoint variables), so its new value is the old one inverted; the partial sums
+// of a clause's updates stay within [0, k] in any order, so the packed nibbles never carry or borrow.
+__device__ __forceinline__ void flip_and_update_counts(const Dims& d, const uint8_t* __restrict__ rec_g, int v,
+                                                       uint32_t* assign, uint32_t* cntw) {
+    const uint16_t* row_off = reinterpret_cast<const uint16_t*>(rec_g + d.csr_off);
+    const uint16_t* occ = row_off + ((d.n + 1 + 7) & ~7);
+    const uint32_t bit = 1u << (v & 31);
+    const uint32_t now_true = ((assign[v >> 5] & bit) == 0u) ? 1u : 0u;      // value after the flip
+    atomicXor(&assign[v >> 5], bit);
+    const int o1 = row_off[v + 1];
+    for (int o = row_off[v]; o < o1; ++o) {
+        const uint32_t code = occ[o];
+        const uint32_t c = code >> 1;
+        const uint32_t unit = 1u << (4 * (c & 7));
+        if ((code & 1u) ^ now_true) atomicAdd(&cntw[c >> 3], unit);           // this literal became true
+        else atomicSub(&cntw[c >> 3], unit);
+    }
+}
+
+template <int GS>
+__device__ __forceinline__ void apply_actions_incr(const Dims& d, const int32_t* __restrict__ actions, int e,
+                                                   const uint8_t* __restrict__ rec_g, uint32_t* assign, uint32_t* cntw,
+                                                   int gt) {
+    if (d.action_mode == 0) {
+        const int32_t* act = actions + (size_t)e * d.A;
+        for (int a = gt; a < d.A; a += GS) {
+            const int x = act[a];
+            const int size = group_size(d, a);
+            if (x >= size) continue;                       // env:236 no-op
+            int idx = x < size - 1 ? x : size - 1;         // env:238
+            if (idx < 0) idx += d.V;                       // JAX gather: wrap once, then clamp
+            idx = idx < 0 ? 0 : (idx > d.V - 1 ? d.V - 1 : idx);
+            if (idx >= size) continue;                     // landed on a -1 pad: one_hot(-1) = 0 (env:243)
+            flip_and_update_counts(d, rec_g, group_start(d, a) + idx, assign, cntw);
+        }
+    } else {
+        const int32_t* act = actions + (size_t)e * d.A * d.V;
+        for (int i = gt; i < d.A * d.V; i += GS) {
+            const int a = i / d.V, j = i - a * d.V;
+            if (j < group_size(d, a) && (act[i] & 1))      // env:246-250 (actions are 0/1)
+                flip_and_update_counts(d, rec_g, group_start(d, a) + j, assign, cntw);
         }
     }
 }
@@ -382,6 +476,20 @@ __device__ __forceinline__ void emit_gnn_assignment(const Dims& d, long long row
                          [&](int v) { return (assign[v >> 5] >> (v & 31)) & 1u; });
 }
 
+// Dispatch on clause width (k == 3 has its own unrolled path) and on whether clause features are wanted.
+template <int GS, bool INCR>
+__device__ __forceinline__ void run_eval(const Dims& d, const uint16_t* lits, const uint8_t* tt, uint32_t* cntw,
+                                         uint32_t* satw, int* nunsat, const float2* cf01, uint8_t* stage, float* cf_row,
+                                         int gid, int gt) {
+    if (cf_row) {
+        if (d.k == 3) eval_clauses_gnn<GS, true, INCR>(d, lits, tt, cntw, satw, nunsat, cf01, stage, cf_row, gid, gt);
+        else eval_clauses_gnn<GS, false, INCR>(d, lits, tt, cntw, satw, nunsat, cf01, stage, cf_row, gid, gt);
+    } else {
+        if (d.k == 3) eval_clauses<GS, true, INCR>(d, lits, tt, cntw, satw, nunsat, gt);
+        else eval_clauses<GS, false, INCR>(d, lits, tt, cntw, satw, nunsat, gt);
+    }
+}
+
 // One rollout step of the rng alone (learner:397,416,426): rng <- split(rng)[0]; rng <- split(rng)[0];
 // rng <- split(rng, 3)[0].
 __device__ __forceinline__ void rng_advance(uint32_t& r0, uint32_t& r1) {
@@ -400,7 +508,7 @@ __device__ __forceinline__ void rng_advance(uint32_t& r0, uint32_t& r1) {
 // 256-thread CTAs, 256/GS envs each.  OBS = the launch writes local observations (whole bank record
 // staged, observation re-basing buffers); !OBS = literal block only, optional GNN-input outputs.
 // =====================================================================================
-template <int GS, int MODE, bool OBS, bool MULTI>
+template <int GS, int MODE, bool OBS, bool MULTI, bool INCR>
 __global__ void __launch_bounds__(kCtaThreads, (MULTI || !OBS) ? 4 : 8) env_kernel(const Dims d, const EnvArgs a) {
     extern __shared__ __align__(128) uint8_t smem_raw[];
     constexpr int NG = kCtaThreads / GS;
@@ -445,7 +553,10 @@ __global__ void __launch_bounds__(kCtaThreads, (MULTI || !OBS) ? 4 : 8) env_kern
     const uint16_t* lits = reinterpret_cast<const uint16_t*>(rec);
     const uint32_t* mflat = reinterpret_cast<const uint32_t*>(rec + d.lits_bytes);
     uint32_t* st_tail = st + d.aw;
-    const uint32_t tma_bytes = OBS ? (uint32_t)d.rec_bytes : (uint32_t)d.lits_bytes;
+    const uint32_t tma_bytes = OBS ? (uint32_t)d.rec_copy_bytes : (uint32_t)d.lits_bytes;
+    // per-clause true-literal counts of an incremental plan live in the state record behind the scalars
+    uint32_t* cntw = d.cnt_words ? st + d.aw + 4 : nullptr;
+    uint32_t* cnt_store = (MODE != MODE_OBS) ? cntw : nullptr;     // full evaluations refresh the counts
     const bool want_cf = !OBS && a.gnn_cf != nullptr;
     float2* cf01 = reinterpret_cast<float2*>(misc + 4);  // {t > 0, t / 3.0} for t = 0..15 true literals (learner:185)
 
@@ -483,23 +594,27 @@ __global__ void __launch_bounds__(kCtaThreads, (MULTI || !OBS) ? 4 : 8) env_kern
         const long long row = (a.emit_every_step ? (long long)j * a.B : 0LL) + e;     // row of obs / GNN outputs
         const long long orow = (long long)j * a.B + e;                                  // row of reward / done / info
 
-        // ---- formula record: TMA bulk copy unless the env's formula is already staged ----
-        if (loaded_pidx != pidx && gt == 0) {
+        // ---- formula record: TMA bulk copy unless the env's formula is already staged (an incremental step
+        //      needs the literals only when the episode restarts) ----
+        if (!INCR && loaded_pidx != pidx && gt == 0) {
             if (j > 0) fence_proxy_async();
             mbar_expect_tx(bar, tma_bytes);
             tma_load_1d(rec, a.bank + (size_t)pidx * d.rec_bytes, tma_bytes, bar);
         }
         if (MODE == MODE_STEP && a.reward_mode) {
             // shaped reward (env:201-223): clause status of the state BEFORE the flips
-            if (loaded_pidx != pidx) {
-                mbar_wait(bar, phase);
-                phase ^= 1u;
-                loaded_pidx = pidx;
+            if (INCR) {
+                run_eval<GS, true>(d, lits, tt, cntw, satw_old, nullptr, cf01, stage, nullptr, gid, gt);
+            } else {
+                if (loaded_pidx != pidx) {
+                    mbar_wait(bar, phase);
+                    phase ^= 1u;
+                    loaded_pidx = pidx;
+                }
+                build_truth_table<GS>(d, st, tt, gt);
+                group_sync<GS>(gid);
+                run_eval<GS, false>(d, lits, tt, nullptr, satw_old, nullptr, cf01, stage, nullptr, gid, gt);
             }
-            build_truth_table<GS>(d, st, tt, gt);
-            group_sync<GS>(gid);
-            if (d.k == 3) eval_clauses<GS, true>(d, lits, tt, satw_old, nullptr, gt);
-            else eval_clauses<GS, false>(d, lits, tt, satw_old, nullptr, gt);
             group_sync<GS>(gid);
         }
 
@@ -507,25 +622,25 @@ __global__ void __launch_bounds__(kCtaThreads, (MULTI || !OBS) ? 4 : 8) env_kern
         if (MODE == MODE_RESET) {
             threefry_assign<GS>(d, a.keys[2 * (size_t)e], a.keys[2 * (size_t)e + 1], st, gt);
         } else if (MODE == MODE_STEP) {
-            apply_actions<GS>(d, a.actions + (long long)j * a.act_step_stride, e, st, gt);
+            if (INCR) apply_actions_incr<GS>(d, a.actions + (long long)j * a.act_step_stride, e,
+                                             a.bank + (size_t)pidx * d.rec_bytes, st, cntw, gt);
+            else apply_actions<GS>(d, a.actions + (long long)j * a.act_step_stride, e, st, gt);
         }
+        if (!INCR && cnt_store)
+            for (int i = gt; i < d.cnt_words; i += GS) cnt_store[i] = 0u;
         group_sync<GS>(gid);
-        build_truth_table<GS>(d, st, tt, gt);
-        if (loaded_pidx != pidx) {
-            mbar_wait(bar, phase);
-            phase ^= 1u;
-            loaded_pidx = pidx;
+        if (!INCR) {
+            build_truth_table<GS>(d, st, tt, gt);
+            if (loaded_pidx != pidx) {
+                mbar_wait(bar, phase);
+                phase ^= 1u;
+                loaded_pidx = pidx;
+            }
+            group_sync<GS>(gid);
         }
-        group_sync<GS>(gid);
 
         float* cf_row = (want_cf && emit) ? a.gnn_cf + row * d.m * 3 : nullptr;
-        if (cf_row) {
-            if (d.k == 3) eval_clauses_gnn<GS, true>(d, lits, tt, satw, &misc[0], cf01, stage, cf_row, gid, gt);
-            else eval_clauses_gnn<GS, false>(d, lits, tt, satw, &misc[0], cf01, stage, cf_row, gid, gt);
-        } else {
-            if (d.k == 3) eval_clauses<GS, true>(d, lits, tt, satw, &misc[0], gt);
-            else eval_clauses<GS, false>(d, lits, tt, satw, &misc[0], gt);
-        }
+        run_eval<GS, INCR>(d, lits, tt, INCR ? cntw : cnt_store, satw, &misc[0], cf01, stage, cf_row, gid, gt);
         group_sync<GS>(gid);
         nunsat = misc[0];
 
@@ -596,6 +711,8 @@ __global__ void __launch_bounds__(kCtaThreads, (MULTI || !OBS) ? 4 : 8) env_kern
                     }
                 }
                 for (int i = gt; i < d.aw; i += GS) st[i] = 0u;
+                if (cnt_store)
+                    for (int i = gt; i < d.cnt_words; i += GS) cnt_store[i] = 0u;
                 group_sync<GS>(gid);
                 threefry_assign<GS>(d, rk0, rk1, st, gt);
                 group_sync<GS>(gid);
@@ -611,12 +728,8 @@ __global__ void __launch_bounds__(kCtaThreads, (MULTI || !OBS) ? 4 : 8) env_kern
                 if (cf_row) {
                     if (gt == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
                     group_sync<GS>(gid);
-                    if (d.k == 3) eval_clauses_gnn<GS, true>(d, lits, tt, satw, &misc[0], cf01, stage, cf_row, gid, gt);
-                    else eval_clauses_gnn<GS, false>(d, lits, tt, satw, &misc[0], cf01, stage, cf_row, gid, gt);
-                } else {
-                    if (d.k == 3) eval_clauses<GS, true>(d, lits, tt, satw, &misc[0], gt);
-                    else eval_clauses<GS, false>(d, lits, tt, satw, &misc[0], gt);
                 }
+                run_eval<GS, false>(d, lits, tt, cnt_store, satw, &misc[0], cf01, stage, cf_row, gid, gt);
                 group_sync<GS>(gid);
                 nunsat = misc[0];
                 step_cur = 0;
@@ -659,11 +772,16 @@ static cudaError_t launch_env_gs(const msat_plan* plan, EnvMode mode, const EnvA
     const int groups = kCtaThreads / GS;
     const int grid = (a.B + groups - 1) / groups;
     if (grid == 0) return cudaSuccess;
-    const void* fns[4] = {(const void*)env_kernel<GS, MODE_RESET, OBS, false>,
-                          (const void*)env_kernel<GS, MODE_STEP, OBS, false>,
-                          (const void*)env_kernel<GS, MODE_OBS, OBS, false>,
-                          (const void*)env_kernel<GS, MODE_STEP, OBS, true>};
+    // incremental clause update: step launches without observations on a plan that carries the counts
+    constexpr int kFns = OBS ? 4 : 6;
+    const void* fns[6] = {(const void*)env_kernel<GS, MODE_RESET, OBS, false, false>,
+                          (const void*)env_kernel<GS, MODE_STEP, OBS, false, false>,
+                          (const void*)env_kernel<GS, MODE_OBS, OBS, false, false>,
+                          (const void*)env_kernel<GS, MODE_STEP, OBS, true, false>,
+                          OBS ? nullptr : (const void*)env_kernel<GS, MODE_STEP, false, false, true>,
+                          OBS ? nullptr : (const void*)env_kernel<GS, MODE_STEP, false, true, true>};
     const bool multi = mode == MODE_STEP && a.num_steps > 1;
+    const bool incr = !OBS && mode == MODE_STEP && plan->d.cnt_words > 0;
     if (multi) smem_bytes += 40 * a.num_steps;
     if (smem_bytes > 48 * 1024) {
         // opt in to > 48 KB of dynamic shared memory once per (plan, device), not once per launch
@@ -672,14 +790,14 @@ static cudaError_t launch_env_gs(const msat_plan* plan, EnvMode mode, const EnvA
         if (err != cudaSuccess) return err;
         const unsigned long long bit = 1ULL << ((OBS ? 0 : 32) + (dev & 31));
         if (!(plan->prepared_devices.load(std::memory_order_acquire) & bit)) {
-            for (const void* f : fns) {
-                err = cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmemOptin);
+            for (int i = 0; i < kFns; ++i) {
+                err = cudaFuncSetAttribute(fns[i], cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmemOptin);
                 if (err != cudaSuccess) return err;
             }
             plan->prepared_devices.fetch_or(bit, std::memory_order_release);
         }
     }
-    const void* fn = fns[multi ? 3 : (mode == MODE_RESET ? 0 : (mode == MODE_STEP ? 1 : 2))];
+    const void* fn = incr ? fns[multi ? 5 : 4] : fns[multi ? 3 : (mode == MODE_RESET ? 0 : (mode == MODE_STEP ? 1 : 2))];
     Dims d = plan->d;
     EnvArgs args = a;
     void* params[] = {&d, &args};

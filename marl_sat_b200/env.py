@@ -86,7 +86,7 @@ def create_agent_groups(num_vars: int, vars_per_agent: Optional[int], verbose: b
 class _Plan:
     """RAII holder of an ``msat_plan*``."""
 
-    def __init__(self, n, m, k, A, action_mode, max_steps, group_threads=0, reward=None):
+    def __init__(self, n, m, k, A, action_mode, max_steps, group_threads=0, reward=None, incremental=False):
         self._lib = _lib.load()
         h = C.c_void_p()
         _lib.check(self._lib.msat_plan_create(C.byref(h), n, m, k, A, action_mode, max_steps, group_threads),
@@ -94,6 +94,8 @@ class _Plan:
         self.handle = h
         if reward is not None:      # (mode, gamma, r_clause, r_sat)
             _lib.check(self._lib.msat_plan_set_reward(h, *reward), "msat_plan_set_reward")
+        if incremental:             # before any bank / state is sized from the dims
+            _lib.check(self._lib.msat_plan_set_clause_update(h, 1), "msat_plan_set_clause_update")
         self.dims = _lib.Dims()
         _lib.check(self._lib.msat_plan_dims(h, C.byref(self.dims)), "msat_plan_dims")
 
@@ -213,7 +215,7 @@ class SATEnv:
     def __init__(self, num_vars, num_clauses, max_steps: int, vars_per_agent: Optional[int] = None,
                  action_mode: int = 0, r_clause: float = 0.02, r_sat: float = 1.0, gamma: float = 0.99,
                  *, device: Union[str, torch.device, None] = None, verbose: bool = True,
-                 group_threads: int = 0, reward_mode: str = "sparse"):
+                 group_threads: int = 0, reward_mode: str = "sparse", clause_update: str = "full"):
         self._lib = _lib.load()
         self.num_vars = int(num_vars)
         self.num_clauses = int(num_clauses)
@@ -227,6 +229,11 @@ class SATEnv:
         if reward_mode not in ("sparse", "shaped"):
             raise ValueError("reward_mode must be 'sparse' or 'shaped'")
         self.reward_mode = reward_mode
+        # "incremental": launches without observations update per-clause true-literal counts from the var ->
+        # clause occurrence lists of the flipped variables instead of re-evaluating every clause (same results)
+        if clause_update not in ("full", "incremental"):
+            raise ValueError("clause_update must be 'full' or 'incremental'")
+        self.clause_update = clause_update
         self.action_mode = int(action_mode)
         self.max_steps = int(max_steps)
         self.max_vars_per_agent = max(len(v) for v in self.agent_groups.values())
@@ -271,7 +278,8 @@ class SATEnv:
         if k not in self._plans:
             reward = (1, float(self.gamma), float(self.r_clause), float(self.r_sat)) if self.reward_mode == "shaped" else None
             self._plans[k] = _Plan(self.num_vars, self.num_clauses, k, self.num_agents, self.action_mode,
-                                   self.max_steps, self._group_threads, reward)
+                                   self.max_steps, self._group_threads, reward,
+                                   incremental=self.clause_update == "incremental")
         return self._plans[k]
 
     def count_resets(self, k: int, counter: Optional[torch.Tensor]) -> None:

@@ -21,8 +21,9 @@ def _random_formulas(rng, B, n, m, k):
     return cl
 
 
+@pytest.mark.parametrize("clause_update", ["full", "incremental"])
 @pytest.mark.parametrize("seed", range(24))
-def test_random_shapes(seed):
+def test_random_shapes(seed, clause_update):
     import marl_sat_b200 as M
     rng = np.random.default_rng(1000 + seed)
     n = int(rng.integers(1, 90))
@@ -38,7 +39,8 @@ def test_random_shapes(seed):
     cl = _random_formulas(rng, B, n, m, k)
     keys = rng.integers(0, 2 ** 32, size=(B, 2), dtype=np.uint64).astype(np.uint32)
     ref = SATEnvOracle(n, m, max_steps, vars_per_agent=vpa, action_mode=mode)
-    env = M.SATEnv(n, m, max_steps, vars_per_agent=vpa, action_mode=mode, verbose=False, group_threads=gs)
+    env = M.SATEnv(n, m, max_steps, vars_per_agent=vpa, action_mode=mode, verbose=False, group_threads=gs,
+                   clause_update=clause_update)
     obs_r, st_r = ref.reset(cl, keys)
     obs_c, st_c = env.reset(cl, keys)
     what = f"[n={n} m={m} k={k} vpa={vpa} mode={mode} B={B} gs={gs}] "
@@ -56,8 +58,9 @@ def test_random_shapes(seed):
         assert np.array_equal(to_np(info_c["num_unsatisfied"]), info_r["num_unsatisfied"])
 
 
+@pytest.mark.parametrize("clause_update", ["full", "incremental"])
 @pytest.mark.parametrize("seed", range(6))
-def test_random_rollouts_with_autoreset(seed):
+def test_random_rollouts_with_autoreset(seed, clause_update):
     import marl_sat_b200 as M
     rng = np.random.default_rng(77 + seed)
     n, m = int(rng.integers(4, 60)), int(rng.integers(5, 120))
@@ -66,7 +69,7 @@ def test_random_rollouts_with_autoreset(seed):
     max_steps = int(rng.integers(1, 4))
     problems = _random_formulas(rng, P, n, m, 3)
     ref = SATEnvOracle(n, m, max_steps, vars_per_agent=vpa)
-    env = M.SATEnv(n, m, max_steps, vars_per_agent=vpa, verbose=False)
+    env = M.SATEnv(n, m, max_steps, vars_per_agent=vpa, verbose=False, clause_update=clause_update)
     key0 = otf.prng_key(seed)
     vec = M.VecSATEnv(env, problems, B, key0)
     obs_c = vec.reset()
@@ -134,3 +137,84 @@ def test_timeout_boundary_stress(gs):
         assert np.array_equal(to_np(done)[sub], done_r)
         assert np.array_equal(to_np(es)[sub], info_r["episode_step"])
     torch.cuda.synchronize()
+
+
+@pytest.mark.parametrize("seed", range(16))
+def test_incremental_clause_update_without_observations(seed):
+    """The incremental (CSR occurrence-list) update only runs in launches that write no observations: rollouts
+    through ``emit_obs=False`` / ``gnn_outputs=True`` -- single steps and K fused steps, interleaved with
+    observation-writing launches on the same state -- against the oracle, on unstructured formulas (repeated
+    variables, x and -x in one clause, 0 padding anywhere), both action modes, every group size."""
+    import marl_sat_b200 as M
+    from oracle import features as ofeat
+    rng = np.random.default_rng(4000 + seed)
+    n, m, k = int(rng.integers(2, 70)), int(rng.integers(1, 300)), int(rng.integers(1, 8))
+    vpa = [None, 1, 3, 5, 7][seed % 5]
+    if vpa is not None and vpa > n:
+        vpa = n
+    mode = seed % 2
+    B, P = int(rng.integers(1, 40)), int(rng.integers(1, 7))
+    gs = [0, 32, 64, 128, 256][(seed // 2) % 5]
+    max_steps = int(rng.integers(1, 5))
+    problems = _random_formulas(rng, P, n, m, k)
+    ref = SATEnvOracle(n, m, max_steps, vars_per_agent=vpa, action_mode=mode)
+    env = M.SATEnv(n, m, max_steps, vars_per_agent=vpa, action_mode=mode, verbose=False, group_threads=gs,
+                   clause_update="incremental")
+    key0 = otf.prng_key(seed)
+    gnn = seed % 3 != 0
+    vec = M.VecSATEnv(env, problems, B, key0, emit_obs=False, gnn_outputs=gnn)
+    vec.reset()
+    key, idx0, rk0 = orollout.initial_reset_inputs(key0, B, P)
+    _, st_r = ref.reset(problems[idx0], rk0)
+    A, V = ref.num_agents, ref.max_vars_per_agent
+    what = f"[n={n} m={m} k={k} vpa={vpa} mode={mode} B={B} gs={gs} gnn={gnn}] "
+
+    def draw(shape_prefix):
+        return (rng.integers(-1, V + 2, size=shape_prefix + (A,)) if mode == 0
+                else rng.integers(0, 2, size=shape_prefix + (A, V))).astype(np.int32)
+
+    def oracle_step(acts):
+        nonlocal key, st_r
+        ks = orollout.rollout_keys(key, B, P)
+        key = ks["rng"]
+        fo, st_r, rew, done, info = orollout.env_step_with_autoreset(ref, st_r, acts, problems,
+                                                                     ks["new_problem_indices"], ks["reset_keys"])
+        return fo, done, info
+
+    for t in range(5):
+        acts = draw((B,))
+        fo, done_r, info_r = oracle_step(acts)
+        out = vec.step(torch.from_numpy(acts).cuda())
+        assert np.array_equal(to_np(out["done"][:, -1]).astype(bool), done_r), what + f"step {t}"
+        assert np.array_equal(to_np(out["num_unsatisfied"]), info_r["num_unsatisfied"]), what + f"step {t}"
+        assert_state_equal(vec.sat_state(), st_r, what + f"step {t} ")
+        if gnn:
+            gs_r = ofeat.state_to_gnn_input(ref, st_r)
+            assert np.array_equal(to_np(out["gnn_assignment"]), gs_r["assignment"])
+            assert np.array_equal(to_np(out["gnn_clause_features"]), gs_r["clause_features"])
+        # an observation-writing launch in between (full evaluation) must leave the counts consistent
+        if t == 2:
+            assert np.array_equal(to_np(env.get_obs_array(vec.sat_state())), fo)
+            acts = draw((B,))
+            fo, done_r, info_r = oracle_step(acts)
+            o2 = env.alloc_step_outputs(B, vec.bank.plan.dims)
+            vec.keys.advance()              # the un-fused path: chain kernel + key derivation + msat_step with obs
+            M.derive_env_keys(vec.keys.prob_key, vec.keys.reset_key, B, 0, B, P, vec.new_problem_idx, vec.reset_keys)
+            env.step_into(vec.bank, vec.state, vec.state, torch.from_numpy(acts).cuda(), o2, auto_reset=True,
+                          new_problem_idx=vec.new_problem_idx, reset_keys=vec.reset_keys)
+            assert np.array_equal(to_np(o2["obs"]), fo), what + "obs-writing step"
+            assert_state_equal(vec.sat_state(), st_r, what + "after the obs-writing step ")
+    # K fused steps
+    K = 6
+    table = draw((K, B))
+    outs = vec.alloc_multi_step_outputs(K, emit_every_step=True)
+    vec.steps(torch.from_numpy(table).cuda(), outs)
+    for j in range(K):
+        fo, done_r, info_r = oracle_step(table[j])
+        assert np.array_equal(to_np(outs["done"][j][:, -1]).astype(bool), done_r), what + f"fused step {j}"
+        assert np.array_equal(to_np(outs["num_unsatisfied"][j]), info_r["num_unsatisfied"]), what + f"fused step {j}"
+        if gnn:
+            gs_r = ofeat.state_to_gnn_input(ref, st_r)
+            assert np.array_equal(to_np(outs["gnn_clause_features"][j]), gs_r["clause_features"]), what + f"fused {j}"
+    assert_state_equal(vec.sat_state(), st_r, what + "after the fused steps ")
+    assert np.array_equal(to_np(env.get_obs_array(vec.sat_state())), fo)
