@@ -675,6 +675,43 @@ def main_ours(args):
                             "block; static graph features emitted once per formula bank; bytes_moved = outputs + "
                             "packed literal block + state r/w + actions + reward/done/info"}
         del vec_g
+        # the same launches with the incremental clause update (north_star: CSR var -> clause occurrence lists,
+        # only the clauses adjacent to flipped variables are touched): its own bank (records carry the CSR) and
+        # state (4-bit true-literal counts per clause); results are bit-identical (tests/test_fuzz_cuda.py)
+        try:
+            env_i = M.SATEnv(w["n"], w["m"], MAX_STEPS, vars_per_agent=w["vpa"], verbose=False, device=dev,
+                             clause_update="incremental")
+            if w["kind"] == "mixed":
+                pr = synth.mixed_ksat_torch(P, w["n"], w["m"], 3, w["k"], seed=20261018 + 2, device=dev)
+            else:
+                pr = synth.uniform_ksat_torch(P, w["n"], w["m"], w["k"], seed=20261018 + 2, device=dev)
+            bank_i = env_i.make_bank(pr, validate=False)
+            del pr
+            legs = {}
+            for label, kw in (("gnn_input", dict(gnn_outputs=True)), ("state_only", dict())):
+                res = {}
+                for variant, (e_, b_) in (("full", (env, bank)), ("incremental", (env_i, bank_i))):
+                    v = M.VecSATEnv(e_, b_, Bg, M.prng_key(SEED + 2), emit_obs=False, compact_outputs=True, **kw)
+                    v.reset()
+                    dephase(v)
+                    for i in range(5):
+                        v.step(actions[i])
+                    torch.cuda.synchronize()
+                    res[variant] = _time_steps(torch, lambda i: v.step(actions[i % ACTION_CYCLE]), Kg) / Kg
+                    del v
+                legs[label] = {"full_ms_per_step": res["full"], "incremental_ms_per_step": res["incremental"],
+                               "incremental_speedup": res["full"] / res["incremental"]}
+            di = bank_i.plan.dims
+            gnn_info["clause_update_variants"] = {
+                **legs, "rec_bytes": {"full": d.rec_bytes, "incremental": di.rec_bytes},
+                "state_bytes": {"full": 4 * d.state_words, "incremental": 4 * di.state_words},
+                "what": "gnn_input: msat_rollout_step_gnn; state_only: msat_rollout_step with obs == NULL (reward / "
+                        "done / info only).  full = every clause re-evaluated from the staged literal block; "
+                        "incremental = +-1 updates of the adjacent clauses' counts from the CSR rows of the flipped "
+                        "variables, no literal block unless the episode restarts"}
+            del bank_i, env_i
+        except torch.OutOfMemoryError:
+            pass
     env.count_resets(w["k"], None)
 
     # ---- reduce over ranks (max time) ------------------------------------------------------------------
@@ -703,7 +740,7 @@ def main_ours(args):
         tf = ROOT / "profiles" / "traffic.json"
         if tf.exists():
             try:
-                rec = json.loads(tf.read_text()).get(f"{wname}:{B}")
+                rec = json.loads(tf.read_text()).get(f"{wname}:{B}")      # committed ncu capture for this shape and batch
                 if rec:
                     traffic = rec["dram_bytes_per_launch"]
                     traffic_src = (f"ncu --set full capture {rec.get('source', 'profiles/')} of this kernel at this "

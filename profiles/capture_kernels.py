@@ -13,7 +13,7 @@ sys.path.insert(0, str(Path(__file__).resolve().parent.parent))
 import marl_sat_b200 as M                       # noqa: E402
 from marl_sat_b200 import _lib, synth            # noqa: E402
 
-which = set(sys.argv[1:]) or {"step", "gnn", "gae", "gae_plain", "norm", "multi"}
+which = set(sys.argv[1:]) or {"step", "gnn", "gae", "gae_plain", "norm", "multi", "incr"}
 dev = torch.device("cuda", 0)
 n, m, k, B, T = 100, 430, 3, 65536, 512
 env = M.SATEnv(n, m, 512, verbose=False, device=dev)
@@ -59,5 +59,30 @@ if which & {"gae", "gae_plain", "norm"}:
     if "norm" in which and adv is not None:
         for i in range(2):
             M.normalize_advantages(adv, stats=stats)
+if "incr" in which:
+    env_i = M.SATEnv(n, m, 512, verbose=False, device=dev, clause_update="incremental")
+    bank_i = env_i.make_bank(synth.uniform_ksat_torch(B, n, m, k, seed=1, device=dev), validate=False)
+    vi = M.VecSATEnv(env_i, bank_i, B, M.prng_key(2), emit_obs=False, compact_outputs=True, gnn_outputs=True)
+    vi.reset()
+    for i in range(3):
+        vi.step(acts[i])
+    del vi, bank_i
+if "shapes" in which:
+    # one observation-writing step launch per (workload, per-GPU batch) for profiles/traffic.json
+    SHAPES = [("uf100-430", 100, 430, 3, None, "uniform", bs) for bs in (32768, 16384, 8192)] + [
+        ("uf50-218", 50, 218, 3, None, "uniform", 4096), ("uf250-1065", 250, 1065, 3, None, "uniform", 16384),
+        ("uf250-1065", 250, 1065, 3, None, "uniform", 2048), ("mixed-k3-7", 100, 430, 7, 7, "mixed", 32768),
+        ("mixed-k3-7", 100, 430, 7, 7, "mixed", 4096), ("uf20-91", 20, 91, 3, None, "uniform", 65536)]
+    for name, n_, m_, k_, vpa, kind, bs in SHAPES:
+        e_ = M.SATEnv(n_, m_, 512, vars_per_agent=vpa, verbose=False, device=dev)
+        pr = (synth.mixed_ksat_torch(bs, n_, m_, 3, k_, seed=1, device=dev) if kind == "mixed"
+              else synth.uniform_ksat_torch(bs, n_, m_, k_, seed=1, device=dev))
+        v_ = M.VecSATEnv(e_, e_.make_bank(pr, validate=False), bs, M.prng_key(1))
+        v_.reset()
+        a_ = torch.randint(0, e_.max_vars_per_agent + 1, (bs, e_.num_agents), generator=g, device=dev, dtype=torch.int32)
+        for i in range(2):
+            v_.step(a_)
+        print("shape", name, bs)
+        del v_, pr
 torch.cuda.synchronize()
 print("ok")
