@@ -229,6 +229,7 @@ int msat_tune(const char* key, int32_t value) {
     if (!key) return MSAT_EINVAL;
     if (!strcmp(key, "gae_plain")) { g_gae_force_plain = value; return MSAT_OK; }
     if (!strcmp(key, "gae_variant")) { g_gae_variant = value; return MSAT_OK; }
+    if (!strcmp(key, "gae_pipe_min_cols")) { g_gae_pipe_min_cols = value; return MSAT_OK; }
     return MSAT_EINVAL;
 }
 

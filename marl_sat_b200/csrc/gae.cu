@@ -112,7 +112,8 @@ __global__ void __launch_bounds__(32 * S) gae_kernel(const float* __restrict__ r
 // recurrences per lane give the instruction-level parallelism that the lower warp count takes away.  No
 // cross-warp synchronisation; per column the arithmetic (and its rounding order) is gae_segment's.
 constexpr int GP_COLS = 128;                // columns per warp (4 per lane)
-int g_gae_variant = 0;                      // msat_tune("gae_variant", v): ring shape, see launch_gae
+int g_gae_variant = 0;                      // msat_tune("gae_variant", 4 | 2 | 1): pin the columns per lane (sweeps)
+int g_gae_pipe_min_cols = 24576;            // smallest batch that takes the pipelined scan; msat_tune("gae_pipe_min_cols", B)
 
 __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem_dst)), "l"(gmem_src) : "memory");
@@ -137,21 +138,33 @@ __device__ __forceinline__ void gae_update(float r, float v, uint32_t dn, float 
     next_value = v;
 }
 
-template <int GP_CH, int GP_NS, int GP_WARPS>
-__global__ void __launch_bounds__(32 * GP_WARPS) gae_pipe_kernel(const float* __restrict__ reward, long long rs_t,
-                                                                 const uint8_t* __restrict__ done,
-                                                                 const float* __restrict__ value,
-                                                                 const float* __restrict__ last_val, float gamma,
-                                                                 float gl, float* __restrict__ adv,
-                                                                 float* __restrict__ targets, int T, int B,
-                                                                 double* __restrict__ stats) {
+// VEC = env columns per lane: 4 (16-byte accesses, 512 contiguous bytes per warp request) for batches of
+// ~50k columns and more, 2 for half of that so that enough warps stay in flight (one warp's 512-step scan is
+// latency-bound on its own: ~70-85 us whatever the batch, profiles/r2_gae_sweep.txt); smaller batches take
+// the time-segmented kernel above.
+template <int VEC>
+__device__ __forceinline__ void cp_async_vec(void* smem_dst, const void* gmem_src) {
+    if (VEC == 4) cp_async16(smem_dst, gmem_src);
+    else if (VEC == 2) asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(smem_dst)), "l"(gmem_src) : "memory");
+    else cp_async4(smem_dst, gmem_src);
+}
+
+template <int GP_CH, int GP_NS, int VEC>
+__global__ void __launch_bounds__(32) gae_pipe_kernel(const float* __restrict__ reward, long long rs_t,
+                                                      const uint8_t* __restrict__ done,
+                                                      const float* __restrict__ value,
+                                                      const float* __restrict__ last_val, float gamma, float gl,
+                                                      float* __restrict__ adv, float* __restrict__ targets, int T, int B,
+                                                      double* __restrict__ stats) {
     extern __shared__ __align__(16) uint8_t gp_smem[];
-    constexpr int GP_STAGE = GP_CH * (GP_COLS * 4 + GP_COLS * 4 + GP_COLS);
-    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    const int b = (blockIdx.x * GP_WARPS + w) * GP_COLS + 4 * lane;      // first of this lane's four columns
-    if (b - 4 * lane >= B) return;                         // whole warp leaves
-    uint8_t* ring = gp_smem + (size_t)w * (GP_NS * GP_STAGE);
-    const bool ok = b < B;                                 // B % 4 == 0: all four columns or none
+    constexpr int COLS = 32 * VEC;
+    constexpr int GP_STAGE = GP_CH * (COLS * 4 + COLS * 4 + COLS);
+    const int lane = threadIdx.x;
+    const int b = blockIdx.x * COLS + VEC * lane;          // first of this lane's VEC columns
+    uint8_t* ring = gp_smem;
+    const bool ok = b < B;                                 // B % 4 == 0 and VEC | 4: all VEC columns or none
+    // the done row travels in 4-byte pieces: every lane (VEC 4), every 2nd (VEC 2) or every 4th lane (VEC 1)
+    const bool d_lane = (lane % (4 / VEC)) == 0;
     const int nchunks = (T + GP_CH - 1) / GP_CH;
 
     // chunk c = time steps T-1-c*GP_CH down to T-c*GP_CH-GP_CH; row i of a stage = step t_hi - i
@@ -163,9 +176,9 @@ __global__ void __launch_bounds__(32 * GP_WARPS) gae_pipe_kernel(const float* __
             for (int i = 0; i < GP_CH; ++i) {
                 const int t = t_hi - i;
                 if (t >= 0) {
-                    cp_async16(st + i * (GP_COLS * 4) + lane * 16, reward + (long long)t * rs_t + b);
-                    cp_async16(st + GP_CH * GP_COLS * 4 + i * (GP_COLS * 4) + lane * 16, value + (size_t)t * B + b);
-                    cp_async4(st + 2 * GP_CH * GP_COLS * 4 + i * GP_COLS + lane * 4, done + (size_t)t * B + b);
+                    cp_async_vec<VEC>(st + i * (COLS * 4) + lane * (4 * VEC), reward + (long long)t * rs_t + b);
+                    cp_async_vec<VEC>(st + GP_CH * COLS * 4 + i * (COLS * 4) + lane * (4 * VEC), value + (size_t)t * B + b);
+                    if (d_lane) cp_async4(st + 2 * GP_CH * COLS * 4 + i * COLS + lane * VEC, done + (size_t)t * B + b);
                 }
             }
         }
@@ -174,15 +187,19 @@ __global__ void __launch_bounds__(32 * GP_WARPS) gae_pipe_kernel(const float* __
 
 #pragma unroll
     for (int c = 0; c < GP_NS - 1; ++c) issue(c);
-    float nv[4] = {0.f, 0.f, 0.f, 0.f}, gae[4] = {0.f, 0.f, 0.f, 0.f};
-    if (ok) {
-        const float4 lv = *reinterpret_cast<const float4*>(last_val + b);
-        nv[0] = lv.x; nv[1] = lv.y; nv[2] = lv.z; nv[3] = lv.w;
+    float nv[VEC], gae[VEC];
+    double ssum[VEC], ssq[VEC];
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) {
+        nv[j] = ok ? __ldg(last_val + b + j) : 0.0f;
+        gae[j] = 0.0f;
+        ssum[j] = 0.0;
+        ssq[j] = 0.0;
     }
-    double ssum[4] = {0.0, 0.0, 0.0, 0.0}, ssq[4] = {0.0, 0.0, 0.0, 0.0};
     for (int c = 0; c < nchunks; ++c) {
         issue(c + GP_NS - 1);
-        cp_async_wait<GP_NS - 1>();                        // chunk c has landed: every lane reads only its own copies
+        cp_async_wait<GP_NS - 1>();                        // chunk c has landed (this lane's copies) ...
+        if (VEC < 4) __syncwarp();                         // ... and the neighbour lane's piece of the done row
         const uint8_t* st = ring + (c % GP_NS) * GP_STAGE;
         const int t_hi = T - 1 - c * GP_CH;
         if (ok) {
@@ -190,23 +207,54 @@ __global__ void __launch_bounds__(32 * GP_WARPS) gae_pipe_kernel(const float* __
             for (int i = 0; i < GP_CH; ++i) {
                 const int t = t_hi - i;
                 if (t >= 0) {
-                    const float4 r4 = *reinterpret_cast<const float4*>(st + i * (GP_COLS * 4) + lane * 16);
-                    const float4 v4 = *reinterpret_cast<const float4*>(st + GP_CH * GP_COLS * 4 + i * (GP_COLS * 4) + lane * 16);
-                    const uint32_t d4 = *reinterpret_cast<const uint32_t*>(st + 2 * GP_CH * GP_COLS * 4 + i * GP_COLS + lane * 4);
-                    float4 a4, g4;
-                    gae_update(r4.x, v4.x, d4 & 0xFFu, gamma, gl, nv[0], gae[0], ssum[0], ssq[0], a4.x, g4.x);
-                    gae_update(r4.y, v4.y, d4 & 0xFF00u, gamma, gl, nv[1], gae[1], ssum[1], ssq[1], a4.y, g4.y);
-                    gae_update(r4.z, v4.z, d4 & 0xFF0000u, gamma, gl, nv[2], gae[2], ssum[2], ssq[2], a4.z, g4.z);
-                    gae_update(r4.w, v4.w, d4 & 0xFF000000u, gamma, gl, nv[3], gae[3], ssum[3], ssq[3], a4.w, g4.w);
-                    __stcs(reinterpret_cast<float4*>(adv + (size_t)t * B + b), a4);
-                    __stcs(reinterpret_cast<float4*>(targets + (size_t)t * B + b), g4);
+                    float r[VEC], v[VEC], a[VEC], g[VEC];
+                    uint32_t dn[VEC];
+                    const uint8_t* pr = st + i * (COLS * 4) + lane * (4 * VEC);
+                    const uint8_t* pv = st + GP_CH * COLS * 4 + i * (COLS * 4) + lane * (4 * VEC);
+                    const uint8_t* pd = st + 2 * GP_CH * COLS * 4 + i * COLS + lane * VEC;
+                    if (VEC == 4) {
+                        const float4 r4 = *reinterpret_cast<const float4*>(pr), v4 = *reinterpret_cast<const float4*>(pv);
+                        const uint32_t d4 = *reinterpret_cast<const uint32_t*>(pd);
+                        r[0] = r4.x; r[1 % VEC] = r4.y; r[2 % VEC] = r4.z; r[3 % VEC] = r4.w;
+                        v[0] = v4.x; v[1 % VEC] = v4.y; v[2 % VEC] = v4.z; v[3 % VEC] = v4.w;
+                        dn[0] = d4 & 0xFFu; dn[1 % VEC] = d4 & 0xFF00u; dn[2 % VEC] = d4 & 0xFF0000u; dn[3 % VEC] = d4 & 0xFF000000u;
+                    } else if (VEC == 2) {
+                        const float2 r2 = *reinterpret_cast<const float2*>(pr), v2 = *reinterpret_cast<const float2*>(pv);
+                        const uint32_t d2 = *reinterpret_cast<const uint16_t*>(pd);
+                        r[0] = r2.x; r[1 % VEC] = r2.y;
+                        v[0] = v2.x; v[1 % VEC] = v2.y;
+                        dn[0] = d2 & 0xFFu; dn[1 % VEC] = d2 & 0xFF00u;
+                    } else {
+                        r[0] = *reinterpret_cast<const float*>(pr);
+                        v[0] = *reinterpret_cast<const float*>(pv);
+                        dn[0] = *pd;
+                    }
+#pragma unroll
+                    for (int j = 0; j < VEC; ++j)
+                        gae_update(r[j], v[j], dn[j], gamma, gl, nv[j], gae[j], ssum[j], ssq[j], a[j], g[j]);
+                    float* pa = adv + (size_t)t * B + b;
+                    float* pt = targets + (size_t)t * B + b;
+                    if (VEC == 4) {
+                        __stcs(reinterpret_cast<float4*>(pa), make_float4(a[0], a[1 % VEC], a[2 % VEC], a[3 % VEC]));
+                        __stcs(reinterpret_cast<float4*>(pt), make_float4(g[0], g[1 % VEC], g[2 % VEC], g[3 % VEC]));
+                    } else if (VEC == 2) {
+                        __stcs(reinterpret_cast<float2*>(pa), make_float2(a[0], a[1 % VEC]));
+                        __stcs(reinterpret_cast<float2*>(pt), make_float2(g[0], g[1 % VEC]));
+                    } else {
+                        __stcs(pa, a[0]);
+                        __stcs(pt, g[0]);
+                    }
                 }
             }
         }
-        // the stage is refilled by this lane's own copies only after its reads above (program order)
+        // the r / v pieces of a stage are refilled only by the lane that read them (program order); the done
+        // pieces of VEC < 4 are shared between neighbouring lanes
+        if (VEC < 4) __syncwarp();
     }
     if (stats) {
-        double s1 = (ssum[0] + ssum[1]) + (ssum[2] + ssum[3]), s2 = (ssq[0] + ssq[1]) + (ssq[2] + ssq[3]);
+        double s1 = 0.0, s2 = 0.0;
+#pragma unroll
+        for (int j = 0; j < VEC; ++j) { s1 += ssum[j]; s2 += ssq[j]; }
         for (int o = 16; o > 0; o >>= 1) {
             s1 += __shfl_xor_sync(0xffffffffu, s1, o);
             s2 += __shfl_xor_sync(0xffffffffu, s2, o);
@@ -214,7 +262,7 @@ __global__ void __launch_bounds__(32 * GP_WARPS) gae_pipe_kernel(const float* __
         if (lane == 0) {
             atomicAdd(&stats[1], s1);
             atomicAdd(&stats[2], s2);
-            if (blockIdx.x == 0 && w == 0) atomicAdd(&stats[0], (double)T * (double)B);
+            if (blockIdx.x == 0) atomicAdd(&stats[0], (double)T * (double)B);
         }
     }
 }
@@ -288,25 +336,14 @@ __global__ void __launch_bounds__(256) adv_normalize_kernel(float* __restrict__ 
     }
 }
 
-template <int CH, int NS, int WARPS>
+template <int CH, int NS, int VEC>
 static cudaError_t launch_gae_pipe(const float* reward, long long rs_t, const uint8_t* done, const float* value,
                                    const float* last_val, float gamma, float gl, float* adv, float* targets, int T, int B,
                                    double* stats, cudaStream_t s) {
-    constexpr int kSmem = WARPS * NS * CH * (GP_COLS * 4 + GP_COLS * 4 + GP_COLS);
-    static_assert(kSmem <= 227 * 1024, "ring does not fit");
-    static std::atomic<unsigned long long> prepared{0};
-    int dev = 0;
-    cudaError_t err = cudaGetDevice(&dev);
-    if (err != cudaSuccess) return err;
-    if (!(prepared.load(std::memory_order_acquire) & (1ULL << (dev & 63)))) {
-        err = cudaFuncSetAttribute((const void*)gae_pipe_kernel<CH, NS, WARPS>,
-                                   cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem);
-        if (err != cudaSuccess) return err;
-        prepared.fetch_or(1ULL << (dev & 63), std::memory_order_release);
-    }
-    const int pgrid = (B + GP_COLS * WARPS - 1) / (GP_COLS * WARPS);
-    gae_pipe_kernel<CH, NS, WARPS><<<pgrid, 32 * WARPS, kSmem, s>>>(reward, rs_t, done, value, last_val, gamma, gl, adv,
-                                                                   targets, T, B, stats);
+    constexpr int kSmem = NS * CH * (32 * VEC * 9);
+    static_assert(kSmem <= 48 * 1024, "ring must fit the default dynamic shared memory limit");
+    gae_pipe_kernel<CH, NS, VEC><<<(B + 32 * VEC - 1) / (32 * VEC), 32, kSmem, s>>>(reward, rs_t, done, value, last_val,
+                                                                                    gamma, gl, adv, targets, T, B, stats);
     return cudaGetLastError();
 }
 
@@ -325,17 +362,13 @@ cudaError_t launch_gae(const float* reward, long long rs_t, long long rs_b, cons
                           reinterpret_cast<uintptr_t>(last_val) | reinterpret_cast<uintptr_t>(adv) |
                           reinterpret_cast<uintptr_t>(targets)) & 15) == 0 &&
                         (reinterpret_cast<uintptr_t>(done) & 3) == 0;
-    if (S == 1 && rows16 && !g_gae_force_plain) {
-        switch (g_gae_variant) {
-            case 1: return launch_gae_pipe<4, 6, 1>(reward, rs_t, done, value, last_val, gamma, gl, adv, targets, T, B, stats, s);
-            case 2: return launch_gae_pipe<4, 8, 1>(reward, rs_t, done, value, last_val, gamma, gl, adv, targets, T, B, stats, s);
-            case 3: return launch_gae_pipe<16, 3, 1>(reward, rs_t, done, value, last_val, gamma, gl, adv, targets, T, B, stats, s);
-            case 4: return launch_gae_pipe<8, 6, 1>(reward, rs_t, done, value, last_val, gamma, gl, adv, targets, T, B, stats, s);
-            case 5: return launch_gae_pipe<8, 3, 1>(reward, rs_t, done, value, last_val, gamma, gl, adv, targets, T, B, stats, s);
-            case 6: return launch_gae_pipe<4, 4, 1>(reward, rs_t, done, value, last_val, gamma, gl, adv, targets, T, B, stats, s);
-            case 7: return launch_gae_pipe<8, 4, 2>(reward, rs_t, done, value, last_val, gamma, gl, adv, targets, T, B, stats, s);
-            default: return launch_gae_pipe<8, 4, 1>(reward, rs_t, done, value, last_val, gamma, gl, adv, targets, T, B, stats, s);
-        }
+    // pipelined scan when the batch keeps enough one-warp CTAs in flight at some column vector width
+    if (rows16 && !g_gae_force_plain && B >= g_gae_pipe_min_cols) {
+        int vec = g_gae_variant;               // msat_tune("gae_variant", 4 | 2 | 1) pins the width (sweeps)
+        if (vec != 4 && vec != 2 && vec != 1) vec = B >= 2 * g_gae_pipe_min_cols ? 4 : 2;
+#define MSAT_PIPE(V) launch_gae_pipe<8, 4, V>(reward, rs_t, done, value, last_val, gamma, gl, adv, targets, T, B, stats, s)
+        return vec == 4 ? MSAT_PIPE(4) : (vec == 2 ? MSAT_PIPE(2) : MSAT_PIPE(1));
+#undef MSAT_PIPE
     }
 #define MSAT_GAE_LAUNCH(SS)                                                                                         \
     gae_kernel<SS><<<grid, 32 * SS, 0, s>>>(reward, rs_t, rs_b, done, value, last_val, gamma, gl, adv, targets, T, B, \

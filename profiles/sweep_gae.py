@@ -15,9 +15,11 @@ value = torch.randn((T, B), generator=g, device=dev)
 last = torch.randn((B,), generator=g, device=dev)
 adv, tgt = torch.empty((T, B), device=dev), torch.empty((T, B), device=dev)
 stats = torch.zeros(3, dtype=torch.float64, device=dev)
-names = {0: "CH8 NS4 W1", 1: "CH4 NS6 W1", 2: "CH4 NS8 W1", 3: "CH16 NS3 W1", 4: "CH8 NS6 W1", 5: "CH8 NS3 W1",
-         6: "CH4 NS4 W1", 7: "CH8 NS4 W2", -1: "plain (register-chunked)"}
-for v in [-1, 0, 1, 2, 3, 4, 5, 6, 7]:
+names = {0: "pipelined, width by batch", 4: "pipelined, 4 columns/lane", 2: "pipelined, 2 columns/lane",
+         1: "pipelined, 1 column/lane", -1: "register-chunked / segmented"}
+if len(sys.argv) > 2:
+    lib.msat_tune(b"gae_pipe_min_cols", int(sys.argv[2]))
+for v in [-1, 0, 4, 2, 1]:
     lib.msat_tune(b"gae_plain", 1 if v < 0 else 0)
     lib.msat_tune(b"gae_variant", max(v, 0))
     for _ in range(3):

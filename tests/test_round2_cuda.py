@@ -197,6 +197,13 @@ def test_gae_pipelined_scan_matches_oracle(T, B, strided):
     finally:
         lib.msat_tune(b"gae_plain", 0)
     assert torch.equal(adv_p, adv_c) and torch.equal(tgt_p, tgt_c)
+    for width in (4, 2, 1):            # every column width of the pipelined kernel (normally chosen by batch size)
+        lib.msat_tune(b"gae_variant", width)
+        try:
+            adv_w, tgt_w = M.calculate_gae(*args, 0.995, 0.95)
+        finally:
+            lib.msat_tune(b"gae_variant", 0)
+        assert torch.equal(adv_w, adv_c) and torch.equal(tgt_w, tgt_c), width
     assert float(stats[0]) == T * B and torch.allclose(stats, stats_p, rtol=1e-12, atol=1e-7)
     norm_r = ogae.normalize_advantages(adv_r)
     norm_c = M.normalize_advantages(adv_c.clone(), stats=stats)
