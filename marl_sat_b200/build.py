@@ -49,5 +49,28 @@ def build(force: bool = False, verbose: bool = False) -> Path:
     return LIB_PATH
 
 
+FFI_SRC = CSRC / "xla_ffi_shim.cc"
+FFI_LIB = CSRC / "libmarlsat_b200_xla.so"
+
+
+def build_ffi_shim() -> Path:
+    """Compile the XLA FFI custom-call layer (csrc/xla_ffi_shim.cc) against the headers JAX ships
+    (``jax.ffi.include_dir()``) and link it to libmarlsat_b200.so.  Only possible where JAX >= 0.4.38 is
+    installed -- it is not in this image, where the shim is syntax-checked against tests/ffi_stub instead."""
+    try:
+        from jax import ffi as jffi
+    except Exception as e:
+        raise RuntimeError("the XLA FFI shim needs JAX (jax.ffi.include_dir()); skipping") from e
+    build()
+    cmd = [_nvcc(), "-O2", "-std=c++17", "-shared", "-Xcompiler", "-fPIC", "-I", jffi.include_dir(), "-o", str(FFI_LIB),
+           str(FFI_SRC), "-L", str(CSRC), "-lmarlsat_b200", "-Xlinker", "-rpath", "-Xlinker", "$ORIGIN"]
+    res = subprocess.run(cmd, cwd=CSRC, capture_output=True, text=True)
+    if res.returncode != 0:
+        raise RuntimeError("building the XLA FFI shim failed:\n" + " ".join(cmd) + "\n" + res.stdout + res.stderr)
+    return FFI_LIB
+
+
 if __name__ == "__main__":
     print(build(force=True, verbose="-v" in sys.argv))
+    if "--ffi" in sys.argv:
+        print(build_ffi_shim())
