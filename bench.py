@@ -584,11 +584,26 @@ def main_ours(args):
             stats.zero_()
             M.calculate_gae(g_reward, g_done, g_value, g_last, 0.995, 0.95, stats=stats, out=(adv, tgt))
 
+        gstats = [stats]
+
         def norm_once():
-            M.normalize_advantages(adv, stats=stats)         # all-reduces the 24-byte statistics when world > 1
+            M.normalize_advantages(adv, stats=gstats[0], reduced=True)    # the kernel alone (statistics already global)
         for _ in range(3):
             scan_once()
         raw = adv.clone()
+        allreduce_us = None
+        if world > 1:
+            # the one collective of the advantage path: NCCL all-reduce of (count, sum, sum of squares), 24 bytes
+            for _ in range(3):
+                gstats[0] = M.allreduce_stats(stats)
+            torch.cuda.synchronize()
+            a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a0.record()
+            for _ in range(20):
+                gstats[0] = M.allreduce_stats(stats)
+            a1.record()
+            torch.cuda.synchronize()
+            allreduce_us = a0.elapsed_time(a1) * 1e3 / 20
         norm_once()
         torch.cuda.synchronize()
         g0, g1, g2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
@@ -623,8 +638,8 @@ def main_ours(args):
                     "normalize_bytes_per_element": 8, "normalize_gbs": 8.0 * T * B / (norm_ms * 1e-3) / 1e9,
                     "note": "synthetic rollout, inputs resident in HBM; 17 B/element = reward 4 + done 1 + value 4 + "
                             "adv 4 + target 4, advantage statistics accumulated in the same pass; normalisation = "
-                            "one in-place map (8 B)" + ("; with world > 1 normalize_ms includes the NCCL all-reduce "
-                                                        "of (count, sum, sum of squares)" if world > 1 else "")}
+                            "one in-place map (8 B) with already reduced statistics",
+                    "stats_allreduce_us": allreduce_us}
         if world > 1 and Bg % world == 0:
             # self-check of the sharded normalisation: gather every rank's raw advantages on rank 0 and compare
             # the sharded result with the full-batch computation

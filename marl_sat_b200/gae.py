@@ -100,7 +100,8 @@ def mean_std_from_stats(stats: torch.Tensor):
     return mean, max(ss / n - mean * mean, 0.0) ** 0.5
 
 
-def normalize_advantages(adv: torch.Tensor, stats: Optional[torch.Tensor] = None, group=None) -> torch.Tensor:
+def normalize_advantages(adv: torch.Tensor, stats: Optional[torch.Tensor] = None, group=None,
+                         reduced: bool = False) -> torch.Tensor:
     """In place ``adv = (adv - mean) / (std + 1e-8)`` with the global population std (learner:530-532).
     ``stats``: the local (count, sum, sum of squares) if ``calculate_gae`` already produced them (saves a
     pass over ``adv``); with ``torch.distributed`` initialised they are all-reduced first (a private copy)."""
@@ -110,7 +111,8 @@ def normalize_advantages(adv: torch.Tensor, stats: Optional[torch.Tensor] = None
     work = adv if adv.is_contiguous() else adv.contiguous()      # a strided view is normalised through a copy ...
     if stats is None:
         stats = advantage_stats(work)
-    stats = allreduce_stats(stats, group)                         # global (count, sum, sum of squares)
+    if not reduced:                                              # reduced=True: `stats` are already global
+        stats = allreduce_stats(stats, group)                    # global (count, sum, sum of squares)
     _lib.check(lib.msat_adv_normalize(_ptr(work), work.numel(), _ptr(stats), _stream_ptr(work.device)),
                "msat_adv_normalize")
     if work is not adv:
