@@ -121,8 +121,10 @@ int finish_plan(msat_plan* p) {
     int gs = p->requested_group_threads;
     // measured on B200 (profiles/r1_group_size_sweep.md): about 16-24 store iterations per thread is the sweet
     // spot -- larger groups idle most lanes in the short per-env phases, smaller ones serialise the stores
-    if (gs == 0) gs = chunks <= 768 ? 32 : (chunks <= 1536 ? 64 : (chunks <= 3072 ? 128 : 256));
-    if (gs != 32 && gs != 64 && gs != 128 && gs != 256) return MSAT_EINVAL;
+    // -- and below ~450 chunks (uf20-91: 164, uf35-149: 384) two envs share a warp (half-warp groups): the fixed
+    // per-env instruction count, not the stores, bounds those shapes (profiles/r2_group_size_sweep.md)
+    if (gs == 0) gs = chunks <= 448 ? 16 : (chunks <= 768 ? 32 : (chunks <= 1536 ? 64 : (chunks <= 3072 ? 128 : 256)));
+    if (gs != 16 && gs != 32 && gs != 64 && gs != 128 && gs != 256) return MSAT_EINVAL;
     const GroupLayout L = group_layout(d, true);
     const int kChain = 40 * kMaxFusedSteps;      // room for the K key chains of a multi-step launch
     // grow the group until one CTA's groups fit in shared memory
@@ -137,7 +139,7 @@ int finish_plan(msat_plan* p) {
     // env and stage only the literal block: one warp per env unless the caller pinned the group size or eight
     // groups do not fit in shared memory
     const GroupLayout Ln = p->layout_noobs;
-    int gn = p->requested_group_threads ? gs : 32;
+    int gn = p->requested_group_threads ? (gs < 32 ? 32 : gs) : 32;      // half-warp groups only with observations
     while (gn < 256 && (long long)Ln.total * (kCtaThreads / gn) + kChain > kMaxSmem) gn *= 2;
     if ((long long)Ln.total * (kCtaThreads / gn) + kChain > kMaxSmem) return MSAT_EUNSUPPORTED;
     p->group_threads_noobs = gn;

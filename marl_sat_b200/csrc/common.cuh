@@ -169,12 +169,21 @@ __device__ __forceinline__ void tma_load_1d(void* smem_dst, const void* gmem_src
 }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
-// Barrier over the GS threads that cooperate on one env.  The named-barrier index must be an
+// Barrier over the GS threads that cooperate on one env (GS = 8 / 16: four / two envs share a warp and synchronise with
+// sub-warp lane masks; their control flow may diverge, e.g. when only one of them auto-resets).  The named-barrier index must be an
 // immediate: with a register index ptxas reserves all 16 hardware barriers for the CTA, which caps
 // the number of resident CTAs per SM.
+// GS < 32: lane mask of the sub-warp group (GS consecutive lanes) this thread belongs to, and its first lane
+template <int GS>
+__device__ __forceinline__ uint32_t subwarp_shift() { return threadIdx.x & (32u - GS) & 31u; }
+template <int GS>
+__device__ __forceinline__ uint32_t subwarp_mask() { return ((1u << GS) - 1u) << subwarp_shift<GS>(); }
+
 template <int GS>
 __device__ __forceinline__ void group_sync(int gid) {
-    if constexpr (GS == 32) {
+    if constexpr (GS < 32) {
+        __syncwarp(subwarp_mask<GS>());                 // the lanes of this warp that own this env
+    } else if constexpr (GS == 32) {
         __syncwarp();
     } else if constexpr (GS == 256) {
         asm volatile("bar.sync 1, 256;" ::: "memory");

@@ -1,6 +1,8 @@
 // Batched SATEnv kernels for sm_100a: formula-bank compiler, reset / step(+auto-reset) / get_obs,
 // and the SATState exporter.  Reference semantics: src/envs/multi_agent_sat_env.py (cited as env:LINE)
 // and src/learners/mappo_gnn_sat_learner.py:422-464 (auto-reset).  See DESIGN.md section 4.
+#include <type_traits>
+
 #include "internal.h"
 
 namespace msat {
@@ -177,12 +179,12 @@ __device__ __forceinline__ uint32_t true_literals(const Dims& d, const uint16_t*
 // True-literal count of clause c for the evaluators below.  INCR: the 4-bit count carried in the state (kept
 // up to date by apply_actions_incr); otherwise from the staged literals, optionally packed into `cnt_store`
 // (zeroed by the caller) so that a state of an incremental plan leaves every kernel with valid counts.
-template <bool K3, bool INCR>
+template <bool K3, bool INCR, bool STORE = true>
 __device__ __forceinline__ uint32_t clause_count(const Dims& d, const uint16_t* lits, const uint8_t* tt,
                                                  uint32_t* cntw, int c) {
     if (INCR) return (cntw[c >> 3] >> (4 * (c & 7))) & 15u;
     const uint32_t cnt = true_literals<K3>(d, lits, tt, c);
-    if (cntw && cnt) atomicOr(&cntw[c >> 3], cnt << (4 * (c & 7)));
+    if (STORE && cntw && cnt) atomicOr(&cntw[c >> 3], cnt << (4 * (c & 7)));
     return cnt;
 }
 
@@ -252,14 +254,43 @@ __device__ __forceinline__ void eval_clauses_gnn(const Dims& d, const uint16_t* 
 }
 
 // Plain evaluation (no clause features): status bits + number of unsatisfied clauses (optional).
-template <int GS, bool K3, bool INCR>
-__device__ __forceinline__ void eval_clauses(const Dims& d, const uint16_t* lits, const uint8_t* tt, uint32_t* cntw,
-                                             uint32_t* satw, int* nunsat, int gt) {
+// STORE: also pack the counts into cntw (plans with the incremental update only).
+template <int GS, bool K3, bool INCR, bool STORE>
+__device__ __forceinline__ void eval_clauses_impl(const Dims& d, const uint16_t* lits, const uint8_t* tt, uint32_t* cntw,
+                                                  uint32_t* satw, int* nunsat, int gt) {
     const int lane = gt & 31;
     int nsat = 0;
+    if constexpr (GS < 32) {
+        // several envs per warp: rounds of GS clauses, ballots over the env's own lanes, status bits stored as
+        // GS-bit pieces of the 32-bit status words (little endian)
+        using piece_t = typename std::conditional<GS == 16, uint16_t, uint8_t>::type;
+        piece_t* piece = reinterpret_cast<piece_t*>(satw);
+        const uint32_t sh = subwarp_shift<GS>();
+        const uint32_t mask = subwarp_mask<GS>();
+        const int full = d.m / GS;                       // rounds in which every lane has a clause
+        int r = 0;
+        for (; r < full; ++r) {
+            const uint32_t cnt = clause_count<K3, INCR, STORE>(d, lits, tt, cntw, r * GS + gt);
+            const uint32_t bits = (__ballot_sync(mask, cnt != 0u) >> sh) & ((1u << GS) - 1u);
+            nsat += __popc(bits);
+            if (gt == 0) piece[r] = (piece_t)bits;
+        }
+        if (full * GS < d.m) {                           // the ragged round
+            const int c = r * GS + gt;
+            const uint32_t cnt = c < d.m ? clause_count<K3, INCR, STORE>(d, lits, tt, cntw, c) : 0u;
+            const uint32_t bits = (__ballot_sync(mask, cnt != 0u) >> sh) & ((1u << GS) - 1u);
+            nsat += __popc(bits);
+            if (gt == 0) piece[r] = (piece_t)bits;
+            ++r;
+        }
+        if (gt == 0)
+            for (; r < (32 / GS) * d.sw; ++r) piece[r] = 0;      // rest of the last status word
+        if (nunsat) *nunsat = d.m - nsat;
+        return;
+    }
     for (int w = gt >> 5; w < d.sw; w += GS / 32) {
         const int c = w * 32 + lane;
-        const uint32_t cnt = c < d.m ? clause_count<K3, INCR>(d, lits, tt, cntw, c) : 0u;
+        const uint32_t cnt = c < d.m ? clause_count<K3, INCR, STORE>(d, lits, tt, cntw, c) : 0u;
         const uint32_t word = __ballot_sync(0xffffffffu, cnt != 0u);
         nsat += __popc(word);
         if (lane == 0) satw[w] = word;
@@ -268,6 +299,12 @@ __device__ __forceinline__ void eval_clauses(const Dims& d, const uint16_t* lits
         if (GS == 32) *nunsat = d.m - nsat;
         else if (lane == 0 && nsat) atomicAdd(nunsat, -nsat);
     }
+}
+template <int GS, bool K3, bool INCR>
+__device__ __forceinline__ void eval_clauses(const Dims& d, const uint16_t* lits, const uint8_t* tt, uint32_t* cntw,
+                                             uint32_t* satw, int* nunsat, int gt) {
+    if (!INCR && cntw) eval_clauses_impl<GS, K3, INCR, true>(d, lits, tt, cntw, satw, nunsat, gt);
+    else eval_clauses_impl<GS, K3, INCR, false>(d, lits, tt, cntw, satw, nunsat, gt);
 }
 
 // assign = randint(key, (n,), 0, 2) (env:162): bit 0 of threefry_2x32(split(key)[1], arange(n)).
@@ -404,7 +441,17 @@ __device__ __forceinline__ void emit_obs(const Dims& d, long long row, const uin
         uint32_t xw = 0u;
         int j = j0 > 0 ? j0 : 0;
         const int jend = (j0 + 32 < d.AD) ? j0 + 32 : d.AD;
-        if (j < jend) {
+        if (d.D >= 32) {
+            // a 32-bit window crosses at most one row boundary: the value stream is X repeated with period D, and
+            // bits before / after the env's range are never stored (their mask bits are zero)
+            const int jj = j0 < 0 ? j0 + d.D : j0;
+            int arow = (int)__umulhi((uint32_t)jj, d.inv_D);
+            if (arow * d.D > jj) --arow;
+            const int p = jj - arow * d.D;                       // 0 <= p < D; X has one clean word past D
+            xw = __funnelshift_r(X[p >> 5], X[(p >> 5) + 1], p & 31);
+            const int rem = d.D - p;
+            if (rem < 32) xw |= X[0] << rem;
+        } else if (j < jend) {
             int arow = (int)__umulhi((uint32_t)j, d.inv_D);     // j / D with a rounded-up reciprocal (+0/+1)
             if (arow * d.D > j) --arow;
             int p = j - arow * d.D;
@@ -481,9 +528,11 @@ template <int GS, bool INCR>
 __device__ __forceinline__ void run_eval(const Dims& d, const uint16_t* lits, const uint8_t* tt, uint32_t* cntw,
                                          uint32_t* satw, int* nunsat, const float2* cf01, uint8_t* stage, float* cf_row,
                                          int gid, int gt) {
-    if (cf_row) {
-        if (d.k == 3) eval_clauses_gnn<GS, true, INCR>(d, lits, tt, cntw, satw, nunsat, cf01, stage, cf_row, gid, gt);
-        else eval_clauses_gnn<GS, false, INCR>(d, lits, tt, cntw, satw, nunsat, cf01, stage, cf_row, gid, gt);
+    if (GS >= 32 && cf_row) {          // half-warp groups exist only for observation-writing launches
+        if constexpr (GS >= 32) {
+            if (d.k == 3) eval_clauses_gnn<GS, true, INCR>(d, lits, tt, cntw, satw, nunsat, cf01, stage, cf_row, gid, gt);
+            else eval_clauses_gnn<GS, false, INCR>(d, lits, tt, cntw, satw, nunsat, cf01, stage, cf_row, gid, gt);
+        }
     } else {
         if (d.k == 3) eval_clauses<GS, true, INCR>(d, lits, tt, cntw, satw, nunsat, gt);
         else eval_clauses<GS, false, INCR>(d, lits, tt, cntw, satw, nunsat, gt);
@@ -562,10 +611,13 @@ __global__ void __launch_bounds__(kCtaThreads, (MULTI || !OBS) ? 4 : 8) env_kern
 
     // ---- stage the state record (plain loads) ----
     if (MODE == MODE_RESET) {
+#pragma unroll 1
         for (int i = gt; i < d.state_words; i += GS) st[i] = 0u;
     } else {
-        const uint32_t* sin = a.state_in + (size_t)e * d.state_words;
-        for (int i = gt; i < d.state_words; i += GS) st[i] = sin[i];
+        // state records are multiples of 16 bytes (state_words % 4 == 0) in a 16-byte aligned array
+        const uint4* sin = reinterpret_cast<const uint4*>(a.state_in + (size_t)e * d.state_words);
+#pragma unroll 1
+        for (int i = gt; i < (d.state_words >> 2); i += GS) reinterpret_cast<uint4*>(st)[i] = sin[i];
     }
     if (gt == 0) {
         misc[0] = d.m;              // #unsatisfied accumulator of multi-warp groups: m minus the satisfied counts
@@ -663,10 +715,16 @@ __global__ void __launch_bounds__(kCtaThreads, (MULTI || !OBS) ? 4 : 8) env_kern
                 const float r_cl = __fmul_rn((float)newly, a.r_clause);
                 r = __fadd_rn(__fadd_rn(r_pbrs, r_cl), solved ? a.r_sat : 0.0f);
             }
-            if (a.reward)
-                for (int i = gt; i < a.reward_cols; i += GS) a.reward[orow * a.reward_cols + i] = r;
-            if (a.done)
-                for (int i = gt; i < a.done_cols; i += GS) a.done[orow * a.done_cols + i] = done ? 1 : 0;
+            if (a.reward) {
+                float* rp = a.reward + orow * a.reward_cols;
+#pragma unroll 1
+                for (int i = gt; i < a.reward_cols; i += GS) rp[i] = r;
+            }
+            if (a.done) {
+                uint8_t* dp = a.done + orow * a.done_cols;
+#pragma unroll 1
+                for (int i = gt; i < a.done_cols; i += GS) dp[i] = done ? 1 : 0;
+            }
             if (gt == 0) {
                 if (a.solved) a.solved[orow] = solved ? 1 : 0;
                 if (a.num_unsat) a.num_unsat[orow] = nunsat;
@@ -762,8 +820,9 @@ __global__ void __launch_bounds__(kCtaThreads, (MULTI || !OBS) ? 4 : 8) env_kern
             st_tail[ST_FLAGS] = flags;                                       // env:171,270
         }
         group_sync<GS>(gid);
-        uint32_t* sout = a.state_out + (size_t)e * d.state_words;
-        for (int i = gt; i < d.state_words; i += GS) sout[i] = st[i];
+        uint4* sout = reinterpret_cast<uint4*>(a.state_out + (size_t)e * d.state_words);
+#pragma unroll 1
+        for (int i = gt; i < (d.state_words >> 2); i += GS) sout[i] = reinterpret_cast<const uint4*>(st)[i];
     }
 }
 
@@ -822,6 +881,7 @@ cudaError_t launch_env(const msat_plan* plan, EnvMode mode, const EnvArgs& a0, c
         }
     }
     switch (gs) {
+        case 16: return launch_env_gs<16, true>(plan, mode, a, s, smem);
         case 32: return launch_env_gs<32, true>(plan, mode, a, s, smem);
         case 64: return launch_env_gs<64, true>(plan, mode, a, s, smem);
         case 128: return launch_env_gs<128, true>(plan, mode, a, s, smem);

@@ -63,7 +63,7 @@ w = csv.writer(sys.stdout)
 print(f"# {kregex} / {mangled}: warp instructions executed and stall samples per source line")
 w.writerow(["total_warp_instructions", tot_i, "total_samples", tot_s])
 w.writerow(["warp_inst", "pct_inst", "samples", "pct_samples", "file:line", "source"])
-for (f, ln), (n, s) in sorted(agg.items(), key=lambda kv: -kv[1][0])[:45]:
+for (f, ln), (n, s) in sorted(agg.items(), key=lambda kv: -kv[1][0])[:int(sys.argv[5]) if len(sys.argv) > 5 else 45]:
     if f not in text:
         cand = list((lib.parent).glob(f)) + list((lib.parent.parent.parent / "include").glob(f))
         text[f] = cand[0].read_text().splitlines() if cand else []

@@ -34,7 +34,7 @@ def test_random_shapes(seed, clause_update):
         vpa = n
     mode = int(rng.integers(0, 2))
     B = int(rng.integers(1, 40))
-    gs = [0, 32, 64, 128, 256][seed % 5]
+    gs = [0, 32, 64, 128, 256, 16][seed % 6]
     max_steps = int(rng.integers(1, 4))
     cl = _random_formulas(rng, B, n, m, k)
     keys = rng.integers(0, 2 ** 32, size=(B, 2), dtype=np.uint64).astype(np.uint32)
@@ -103,7 +103,7 @@ def test_empty_batch_is_a_no_op():
 
 
 @pytest.mark.timeout(300, method="thread")
-@pytest.mark.parametrize("gs", [0, 64, 256])
+@pytest.mark.parametrize("gs", [0, 16, 32, 256])
 def test_timeout_boundary_stress(gs):
     """Many envs, tiny max_steps: every env crosses the time-out boundary again and again, so every CTA
     repeatedly takes the 'one step before time-out' and the reset path.  Regression test for a
@@ -154,7 +154,7 @@ def test_incremental_clause_update_without_observations(seed):
         vpa = n
     mode = seed % 2
     B, P = int(rng.integers(1, 40)), int(rng.integers(1, 7))
-    gs = [0, 32, 64, 128, 256][(seed // 2) % 5]
+    gs = [0, 32, 64, 128, 256, 16][(seed // 2) % 6]
     max_steps = int(rng.integers(1, 5))
     problems = _random_formulas(rng, P, n, m, k)
     ref = SATEnvOracle(n, m, max_steps, vars_per_agent=vpa, action_mode=mode)

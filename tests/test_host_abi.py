@@ -60,7 +60,7 @@ def test_plan_dims():
     assert (d.n, d.m, d.k, d.A, d.V, d.D) == (100, 430, 3, 25, 4, 630)
     assert d.rec_bytes % 128 == 0 and d.rec_bytes >= 430 * 3 * 2 + (25 * 630 + 7) // 8
     assert d.state_words % 4 == 0 and d.state_words >= 4 + 4
-    assert d.group_threads in (32, 64, 128, 256) and 0 < d.smem_bytes <= 227 * 1024
+    assert d.group_threads in (16, 32, 64, 128, 256) and 0 < d.smem_bytes <= 227 * 1024
     lib = _lib.load()
     h = C.c_void_p()
     assert lib.msat_plan_create(C.byref(h), 0, 1, 3, 1, 0, 1, 0) == _lib.MSAT_EINVAL
@@ -178,9 +178,10 @@ def test_dimacs_native_argument_validation():
 
 
 def test_plan_groups_for_baseline_shapes():
-    """Group sizes chosen by msat_plan_create for the BASELINE shapes (profiles/r1_group_size_sweep.md)."""
-    expect = {(20, 91, None): 32, (50, 218, None): 32, (100, 430, None): 256, (250, 1065, None): 256,
-              (100, 430, 7): 128, (35, 149, 7): 32}
+    """Group sizes chosen by msat_plan_create for the BASELINE shapes (profiles/r1_group_size_sweep.md,
+    profiles/r2_group_size_sweep.md): half-warp groups (two envs per warp) for the smallest observations."""
+    expect = {(20, 91, None): 16, (50, 218, None): 32, (100, 430, None): 256, (250, 1065, None): 256,
+              (100, 430, 7): 128, (35, 149, 7): 16}
     for (n, m, vpa), gs in expect.items():
         env = M.SATEnv(n, m, 512, vars_per_agent=vpa, verbose=False, device="cpu")
         assert env._plan_for(3).dims.group_threads == gs, (n, m, vpa)

@@ -40,6 +40,10 @@ def _actions(rng, env, shape_prefix):
     (100, 430, 3, None, "uniform", 0, 0, 19, 5, 2),        # 256-thread groups
     (100, 430, 7, 7, "mixed", 0, 128, 11, 6, 3),           # padding quirk shape, 128-thread groups
     (12, 20, 3, None, "uniform", 0, 0, 64, 64, 6),         # K at its maximum, frequent solves
+    (20, 91, 3, None, "uniform", 0, 16, 77, 9, 3),         # half-warp groups: two envs per warp, resets diverge
+    (12, 20, 3, None, "uniform", 1, 16, 35, 33, 4),
+    (20, 91, 3, None, "uniform", 0, 32, 77, 9, 3),         # the same shape with one-warp groups
+    (35, 149, 3, 7, "uniform", 1, 16, 41, 12, 4),
 ])
 @pytest.mark.parametrize("every", [True, False])
 def test_multi_step_launch_equals_single_steps(n, m, k, vpa, kind, mode, gs, B, K, max_steps, every):
