@@ -705,19 +705,27 @@ def main_ours(args):
             bank_i = env_i.make_bank(pr, validate=False)
             del pr
             legs = {}
-            for label, kw in (("gnn_input", dict(gnn_outputs=True)), ("state_only", dict())):
+            # a second action distribution: a policy that mostly waits -- every agent picks the no-op action V
+            # with probability 0.95, so ~1.25 of the 25 agents flip per step (uniform actions: ~20)
+            noop = torch.rand((ACTION_CYCLE, B, A), generator=gen, device=dev) < 0.95
+            sparse = torch.where(noop, torch.full_like(actions, V), actions)
+            del noop
+            for label, kw, acts in (("gnn_input", dict(gnn_outputs=True), actions), ("state_only", dict(), actions),
+                                    ("gnn_input_sparse_flips", dict(gnn_outputs=True), sparse),
+                                    ("state_only_sparse_flips", dict(), sparse)):
                 res = {}
                 for variant, (e_, b_) in (("full", (env, bank)), ("incremental", (env_i, bank_i))):
                     v = M.VecSATEnv(e_, b_, Bg, M.prng_key(SEED + 2), emit_obs=False, compact_outputs=True, **kw)
                     v.reset()
                     dephase(v)
                     for i in range(5):
-                        v.step(actions[i])
+                        v.step(acts[i])
                     torch.cuda.synchronize()
-                    res[variant] = _time_steps(torch, lambda i: v.step(actions[i % ACTION_CYCLE]), Kg) / Kg
+                    res[variant] = _time_steps(torch, lambda i: v.step(acts[i % ACTION_CYCLE]), Kg) / Kg
                     del v
                 legs[label] = {"full_ms_per_step": res["full"], "incremental_ms_per_step": res["incremental"],
                                "incremental_speedup": res["full"] / res["incremental"]}
+            del sparse
             di = bank_i.plan.dims
             gnn_info["clause_update_variants"] = {
                 **legs, "rec_bytes": {"full": d.rec_bytes, "incremental": di.rec_bytes},
@@ -725,7 +733,8 @@ def main_ours(args):
                 "what": "gnn_input: msat_rollout_step_gnn; state_only: msat_rollout_step with obs == NULL (reward / "
                         "done / info only).  full = every clause re-evaluated from the staged literal block; "
                         "incremental = +-1 updates of the adjacent clauses' counts from the CSR rows of the flipped "
-                        "variables, no literal block unless the episode restarts"}
+                        "variables, no literal block unless the episode restarts; *_sparse_flips = 95 % of the agents choose "
+                        "the no-op action (~1.25 flips per env-step instead of ~20)"}
             del bank_i, env_i
         except torch.OutOfMemoryError:
             pass

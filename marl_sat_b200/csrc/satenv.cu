@@ -188,7 +188,7 @@ __device__ __forceinline__ uint32_t clause_count(const Dims& d, const uint16_t* 
     return cnt;
 }
 
-template <int GS, bool K3, bool INCR>
+template <int GS, bool K3, bool INCR, bool STORE>
 __device__ __forceinline__ void eval_clauses_gnn(const Dims& d, const uint16_t* lits, const uint8_t* tt, uint32_t* cntw,
                                                  uint32_t* satw, int* nunsat, const float2* cf01, uint8_t* stage,
                                                  float* __restrict__ cf_out, int gid, int gt) {
@@ -209,7 +209,7 @@ __device__ __forceinline__ void eval_clauses_gnn(const Dims& d, const uint16_t* 
         float* o = reinterpret_cast<float*>(stage + phase16) + 3 * (32 * (gt >> 5) + lane);
         int w = w0 + (gt >> 5);
         for (; w < min(wend, full); w += GS / 32, o += 3 * GS) {
-            const uint32_t cnt = clause_count<K3, INCR>(d, lits, tt, cntw, w * 32 + lane);
+            const uint32_t cnt = clause_count<K3, INCR, STORE>(d, lits, tt, cntw, w * 32 + lane);
             const float2 f = cf01[cnt];
             o[0] = f.x;
             o[1] = f.y;
@@ -222,7 +222,7 @@ __device__ __forceinline__ void eval_clauses_gnn(const Dims& d, const uint16_t* 
             const int c = w * 32 + lane;
             uint32_t cnt = 0u;
             if (c < d.m) {
-                cnt = clause_count<K3, INCR>(d, lits, tt, cntw, c);
+                cnt = clause_count<K3, INCR, STORE>(d, lits, tt, cntw, c);
                 const float2 f = cf01[cnt];
                 o[0] = f.x;
                 o[1] = f.y;
@@ -530,8 +530,14 @@ __device__ __forceinline__ void run_eval(const Dims& d, const uint16_t* lits, co
                                          int gid, int gt) {
     if (GS >= 32 && cf_row) {          // half-warp groups exist only for observation-writing launches
         if constexpr (GS >= 32) {
-            if (d.k == 3) eval_clauses_gnn<GS, true, INCR>(d, lits, tt, cntw, satw, nunsat, cf01, stage, cf_row, gid, gt);
-            else eval_clauses_gnn<GS, false, INCR>(d, lits, tt, cntw, satw, nunsat, cf01, stage, cf_row, gid, gt);
+            const bool store = !INCR && cntw != nullptr;       // pack the counts for an incremental plan's state
+            if (d.k == 3) {
+                if (store) eval_clauses_gnn<GS, true, INCR, true>(d, lits, tt, cntw, satw, nunsat, cf01, stage, cf_row, gid, gt);
+                else eval_clauses_gnn<GS, true, INCR, false>(d, lits, tt, cntw, satw, nunsat, cf01, stage, cf_row, gid, gt);
+            } else {
+                if (store) eval_clauses_gnn<GS, false, INCR, true>(d, lits, tt, cntw, satw, nunsat, cf01, stage, cf_row, gid, gt);
+                else eval_clauses_gnn<GS, false, INCR, false>(d, lits, tt, cntw, satw, nunsat, cf01, stage, cf_row, gid, gt);
+            }
         }
     } else {
         if (d.k == 3) eval_clauses<GS, true, INCR>(d, lits, tt, cntw, satw, nunsat, gt);
