@@ -189,7 +189,8 @@ int msat_plan_create(msat_plan** out, int32_t n, int32_t m, int32_t k, int32_t A
     d.fw = (d.AD + 31) / 32;
     d.agw = (A + 31) / 32;
     d.inv_D = (uint32_t)(((1ULL << 32) + (uint64_t)d.D - 1) / (uint64_t)d.D);
-    d.lits_bytes = (m * k * 2 + 15) & ~15;
+    d.ms = (m + 1) & ~1;
+    d.lits_bytes = (d.ms * k * 2 + 15) & ~15;
     p->requested_group_threads = group_threads;
     const int rc = finish_plan(p);
     if (rc != MSAT_OK) { delete p; return rc; }

@@ -8,6 +8,7 @@ namespace msat {
 // Device-side view of a plan; passed by value to every kernel.
 struct Dims {
     int n, m, k, A, V, D, AD;
+    int ms;               // literal-column stride inside a bank record: m rounded up to even (32-bit paired loads)
     int action_mode, max_steps;
     int base, rem;        // contiguous balanced grouping: size_a = base + (a < rem)
     int aw, sw, xw, fw;   // words: assignment, clause status, obs value vector (+1 pad), flat mask stream
@@ -29,9 +30,10 @@ enum { ST_STEP = 0, ST_PIDX = 1, ST_NUNSAT = 2, ST_FLAGS = 3 };
 // the per-env literal truth table tt[code] (2n + 1 bytes, tt[2n] = 0) answers it without a special case.
 __host__ __device__ __forceinline__ uint32_t lit_pad(const Dims& d) { return 2u * (uint32_t)d.n; }
 
-// Literal codes are stored literal-major ([k][m]) inside a bank record: consecutive lanes = consecutive
-// clauses read consecutive u16 (conflict-free shared-memory loads).
-__host__ __device__ __forceinline__ int lit_index(int m, int c, int j) { return j * m + c; }
+// Literal codes are stored literal-major ([k][ms], ms = m rounded up to even, the spare column holds padding
+// codes) inside a bank record: consecutive lanes = consecutive clauses read consecutive u16 (conflict-free
+// shared-memory loads), and one aligned 32-bit load fetches the codes of two adjacent clauses.
+__host__ __device__ __forceinline__ int lit_index(int ms, int c, int j) { return j * ms + c; }
 
 // ---- agent grouping (env:294-338; contiguous balanced split) --------------
 __host__ __device__ __forceinline__ int group_size(const Dims& d, int a) { return d.base + (a < d.rem ? 1 : 0); }

@@ -23,7 +23,7 @@ __global__ void __launch_bounds__(256) gnn_static_kernel(const Dims d, const uin
     __syncthreads();
     for (int c = tid; c < d.m; c += nt) {            // one thread owns column c of A_pos / A_neg
         for (int j = 0; j < d.k; ++j) {
-            const uint32_t code = lits[lit_index(d.m, c, j)];
+            const uint32_t code = lits[lit_index(d.ms, c, j)];
             if (code == lit_pad(d)) continue;
             const int v = (int)(code >> 1), neg = (int)(code & 1u);
             atomicAdd(&deg[neg * d.n + v], 1);
@@ -58,7 +58,7 @@ __global__ void __launch_bounds__(128) gnn_dynamic_kernel(const Dims d, const ui
         for (int c = tid; c < d.m; c += nt) {
             int ntrue = 0;
             for (int j = 0; j < d.k; ++j) {
-                const uint32_t code = lits[lit_index(d.m, c, j)];
+                const uint32_t code = lits[lit_index(d.ms, c, j)];
                 if (code != lit_pad(d)) {
                     const uint32_t v = code >> 1;
                     ntrue += (int)(((st[v >> 5] >> (v & 31)) ^ code) & 1u);
@@ -145,17 +145,17 @@ __global__ void __launch_bounds__(128) flip_gain_kernel(const Dims d, const uint
     for (int c = tid; c < d.m; c += nt) {
         int ntrue = 0;
         for (int j = 0; j < d.k; ++j) {
-            const uint32_t code = lits[lit_index(d.m, c, j)];
+            const uint32_t code = lits[lit_index(d.ms, c, j)];
             if (code != lit_pad(d)) ntrue += (int)(((st[(code >> 1) >> 5] >> ((code >> 1) & 31)) ^ code) & 1u);
         }
         for (int j = 0; j < d.k; ++j) {
-            const uint32_t code = lits[lit_index(d.m, c, j)];
+            const uint32_t code = lits[lit_index(d.ms, c, j)];
             if (code == lit_pad(d)) continue;
             const uint32_t v = code >> 1;
             bool first = true;              // handle each distinct variable of the clause once
             int true_on_v = 0, false_on_v = 0;
             for (int i = 0; i < d.k; ++i) {
-                const uint32_t ci = lits[lit_index(d.m, c, i)];
+                const uint32_t ci = lits[lit_index(d.ms, c, i)];
                 if (ci == lit_pad(d) || (ci >> 1) != v) continue;
                 if (i < j) first = false;
                 const int t = (int)(((st[v >> 5] >> (v & 31)) ^ ci) & 1u);

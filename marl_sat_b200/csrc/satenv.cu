@@ -25,7 +25,7 @@ __global__ void __launch_bounds__(256) compile_bank_kernel(Dims d, const int32_t
     uint32_t* mflat = reinterpret_cast<uint32_t*>(rec + d.lits_bytes);
 
     for (int i = tid; i < (d.m + d.n) * d.agw; i += nt) csm[i] = 0u;
-    for (int i = d.m * d.k + tid; i < d.lits_bytes / 2; i += nt) lits[i] = lit_pad(d);
+    for (int i = tid; i < d.lits_bytes / 2; i += nt) lits[i] = lit_pad(d);     // spare column and tail stay padding
     for (int i = d.lits_bytes / 4 + d.fw + 1 + tid; i < d.rec_bytes / 4; i += nt)
         reinterpret_cast<uint32_t*>(rec)[i] = 0u;
     __syncthreads();
@@ -48,14 +48,14 @@ __global__ void __launch_bounds__(256) compile_bank_kernel(Dims d, const int32_t
                 const int a = var_to_agent(d, v);
                 ca[a >> 5] |= 1u << (a & 31);
             }
-            lits[lit_index(d.m, c, j)] = code;
+            lits[lit_index(d.ms, c, j)] = code;
         }
     }
     __syncthreads();
     // env:116-121: every real variable of a related clause is a candidate neighbour.
     for (int c = tid; c < d.m; c += nt) {
         for (int j = 0; j < d.k; ++j) {
-            const uint16_t code = lits[lit_index(d.m, c, j)];
+            const uint16_t code = lits[lit_index(d.ms, c, j)];
             if (code == lit_pad(d)) continue;
             const int v = code >> 1;
             for (int w = 0; w < d.agw; ++w) {
@@ -94,7 +94,7 @@ __global__ void __launch_bounds__(256) compile_bank_kernel(Dims d, const int32_t
         for (int i = tid; i <= d.n; i += nt) cnt[i] = 0;
         __syncthreads();
         for (int i = tid; i < d.m * d.k; i += nt) {
-            const uint32_t code = lits[lit_index(d.m, i / d.k, i % d.k)];
+            const uint32_t code = lits[lit_index(d.ms, i / d.k, i % d.k)];
             if (code != lit_pad(d)) atomicAdd(&cnt[code >> 1], 1);
         }
         __syncthreads();
@@ -113,7 +113,7 @@ __global__ void __launch_bounds__(256) compile_bank_kernel(Dims d, const int32_t
             int o = cnt[v];
             for (int i = 0; i < d.m * d.k; ++i) {
                 const int c = i / d.k;
-                const uint32_t code = lits[lit_index(d.m, c, i - c * d.k)];
+                const uint32_t code = lits[lit_index(d.ms, c, i - c * d.k)];
                 if (code != lit_pad(d) && (int)(code >> 1) == v) occ[o++] = (uint16_t)((c << 1) | (code & 1u));
             }
         }
@@ -166,12 +166,12 @@ constexpr int kCfStageClauses = 256;
 template <bool K3>
 __device__ __forceinline__ uint32_t true_literals(const Dims& d, const uint16_t* lits, const uint8_t* tt, int c) {
     if (K3) {
-        const uint32_t l0 = lits[c], l1 = lits[d.m + c], l2 = lits[2 * d.m + c];     // independent loads first
+        const uint32_t l0 = lits[c], l1 = lits[d.ms + c], l2 = lits[2 * d.ms + c];   // independent loads first
         return (uint32_t)tt[l0] + tt[l1] + tt[l2];
     }
     uint32_t cnt = 0u;
 #pragma unroll 4
-    for (int j = 0; j < d.k; ++j) cnt += tt[lits[lit_index(d.m, c, j)]];
+    for (int j = 0; j < d.k; ++j) cnt += tt[lits[lit_index(d.ms, c, j)]];
     return cnt;
 }
 
@@ -251,6 +251,79 @@ __device__ __forceinline__ void eval_clauses_gnn(const Dims& d, const uint16_t* 
     // every lane of a warp holds the same count; one-warp groups need no shared accumulator
     if (GS == 32) *nunsat = d.m - nsat;
     else if (lane == 0 && nsat) atomicAdd(nunsat, -nsat);
+}
+
+// Paired evaluation for k == 3 in launches without observations: a lane owns two ADJACENT clauses, so one aligned
+// 32-bit load fetches both codes of a literal column (3 loads instead of 6), the six feature floats of the pair
+// are contiguous in the staging buffer (three 8-byte stores when the destination phase allows) and the number of
+// satisfied clauses is a per-lane sum reduced once per warp -- no ballots, and no status words: nothing in such a
+// launch reads them (callers that do -- shaped reward, incremental plans -- take the lane = clause evaluators).
+template <int GS, bool CF>
+__device__ __forceinline__ void eval_clauses_pairs(const Dims& d, const uint16_t* lits, const uint8_t* tt, int* nunsat,
+                                                   const float2* cf01, uint8_t* stage, float* __restrict__ cf_out,
+                                                   int gid, int gt) {
+    const uint32_t* l32 = reinterpret_cast<const uint32_t*>(lits);
+    const int ms2 = d.ms >> 1;
+    int nsat = 0;
+    auto counts = [&](int pp, uint32_t& ca, uint32_t& cb) {       // pair pp = clauses 2pp, 2pp + 1
+        const uint32_t w0 = l32[pp], w1 = l32[ms2 + pp], w2 = l32[2 * ms2 + pp];
+        ca = (uint32_t)tt[w0 & 0xFFFFu] + tt[w1 & 0xFFFFu] + tt[w2 & 0xFFFFu];
+        cb = (uint32_t)tt[w0 >> 16] + tt[w1 >> 16] + tt[w2 >> 16];    // spare column of an odd m: padding codes, 0
+        nsat += (ca != 0u) + (cb != 0u);
+    };
+    if constexpr (!CF) {
+        const int npairs = (d.m + 1) >> 1;
+        for (int pp = gt; pp < npairs; pp += GS) {
+            uint32_t ca, cb;
+            counts(pp, ca, cb);
+        }
+    } else {
+        for (int c0 = 0; c0 < d.m; c0 += kCfStageClauses) {
+            const int c1 = min(d.m, c0 + kCfStageClauses);
+            uint8_t* gdst = reinterpret_cast<uint8_t*>(cf_out + 3 * (size_t)c0);
+            const uint32_t phase16 = (uint32_t)(reinterpret_cast<uintptr_t>(gdst) & 15u);
+            if (c0 > 0) {
+                if (gt == 0) tma_store_wait_read();        // the previous pass has left the staging buffer
+                group_sync<GS>(gid);
+            }
+            const bool wide = (phase16 & 7u) == 0u;
+            const int npass = (c1 - c0 + 1) >> 1;            // pairs of this pass (the last may be half valid)
+            for (int q = gt; q < npass; q += GS) {
+                uint32_t ca, cb;
+                counts((c0 >> 1) + q, ca, cb);
+                const float2 f = cf01[ca], g = cf01[cb];
+                float* o = reinterpret_cast<float*>(stage + phase16 + 24 * q);
+                if (wide) {
+                    reinterpret_cast<float2*>(o)[0] = f;
+                    reinterpret_cast<float2*>(o)[1] = make_float2(1.0f, g.x);
+                    reinterpret_cast<float2*>(o)[2] = make_float2(g.y, 1.0f);
+                } else {
+                    o[0] = f.x; o[1] = f.y; o[2] = 1.0f;
+                    o[3] = g.x; o[4] = g.y; o[5] = 1.0f;
+                }
+            }
+            fence_proxy_async();                           // staged floats -> visible to the bulk-copy engine
+            group_sync<GS>(gid);
+            const uint32_t len = 12u * (uint32_t)(c1 - c0);
+            uint32_t head = (16u - phase16) & 15u;
+            head = head < len ? head : len;
+            const uint32_t body = (len - head) & ~15u;
+            if (gt == 0 && body) {
+                tma_store_1d(gdst + head, stage + phase16 + head, body);
+                tma_store_commit();
+            }
+            if (gt >= 1 && gt < 8) {                        // scalar head (lanes 1-3) and tail (lanes 4-6)
+                const uint32_t i = gt < 4 ? (uint32_t)(gt - 1) * 4u : head + body + (uint32_t)(gt - 4) * 4u;
+                const bool mine = gt < 4 ? i < head : i < len;
+                if (mine) *reinterpret_cast<float*>(gdst + i) = *reinterpret_cast<const float*>(stage + phase16 + i);
+            }
+        }
+    }
+    nsat = __reduce_add_sync(0xffffffffu, nsat);
+    if (nunsat) {
+        if (GS == 32) *nunsat = d.m - nsat;
+        else if ((gt & 31) == 0 && nsat) atomicAdd(nunsat, -nsat);
+    }
 }
 
 // Plain evaluation (no clause features): status bits + number of unsatisfied clauses (optional).
@@ -524,10 +597,18 @@ __device__ __forceinline__ void emit_gnn_assignment(const Dims& d, long long row
 }
 
 // Dispatch on clause width (k == 3 has its own unrolled path) and on whether clause features are wanted.
-template <int GS, bool INCR>
+// pairs: the launch writes no observations and nothing reads the clause-status words (see eval_clauses_pairs).
+template <int GS, bool INCR, bool OBS>
 __device__ __forceinline__ void run_eval(const Dims& d, const uint16_t* lits, const uint8_t* tt, uint32_t* cntw,
                                          uint32_t* satw, int* nunsat, const float2* cf01, uint8_t* stage, float* cf_row,
-                                         int gid, int gt) {
+                                         bool pairs, int gid, int gt) {
+    if constexpr (!OBS && !INCR && GS >= 32) {
+        if (pairs) {
+            if (cf_row) eval_clauses_pairs<GS, true>(d, lits, tt, nunsat, cf01, stage, cf_row, gid, gt);
+            else eval_clauses_pairs<GS, false>(d, lits, tt, nunsat, cf01, stage, cf_row, gid, gt);
+            return;
+        }
+    }
     if (GS >= 32 && cf_row) {          // half-warp groups exist only for observation-writing launches
         if constexpr (GS >= 32) {
             const bool store = !INCR && cntw != nullptr;       // pack the counts for an incremental plan's state
@@ -613,6 +694,8 @@ __global__ void __launch_bounds__(kCtaThreads, (MULTI || !OBS) ? 4 : 8) env_kern
     uint32_t* cntw = d.cnt_words ? st + d.aw + 4 : nullptr;
     uint32_t* cnt_store = (MODE != MODE_OBS) ? cntw : nullptr;     // full evaluations refresh the counts
     const bool want_cf = !OBS && a.gnn_cf != nullptr;
+    // k == 3 launches without observations whose clause-status words nobody reads: paired evaluation
+    const bool pairs = !OBS && d.k == 3 && cnt_store == nullptr && cntw == nullptr && a.reward_mode == 0;
     float2* cf01 = reinterpret_cast<float2*>(misc + 4);  // {t > 0, t / 3.0} for t = 0..15 true literals (learner:185)
 
     // ---- stage the state record (plain loads) ----
@@ -662,7 +745,7 @@ __global__ void __launch_bounds__(kCtaThreads, (MULTI || !OBS) ? 4 : 8) env_kern
         if (MODE == MODE_STEP && a.reward_mode) {
             // shaped reward (env:201-223): clause status of the state BEFORE the flips
             if (INCR) {
-                run_eval<GS, true>(d, lits, tt, cntw, satw_old, nullptr, cf01, stage, nullptr, gid, gt);
+                run_eval<GS, true, OBS>(d, lits, tt, cntw, satw_old, nullptr, cf01, stage, nullptr, false, gid, gt);
             } else {
                 if (loaded_pidx != pidx) {
                     mbar_wait(bar, phase);
@@ -671,7 +754,7 @@ __global__ void __launch_bounds__(kCtaThreads, (MULTI || !OBS) ? 4 : 8) env_kern
                 }
                 build_truth_table<GS>(d, st, tt, gt);
                 group_sync<GS>(gid);
-                run_eval<GS, false>(d, lits, tt, nullptr, satw_old, nullptr, cf01, stage, nullptr, gid, gt);
+                run_eval<GS, false, OBS>(d, lits, tt, nullptr, satw_old, nullptr, cf01, stage, nullptr, false, gid, gt);
             }
             group_sync<GS>(gid);
         }
@@ -698,7 +781,7 @@ __global__ void __launch_bounds__(kCtaThreads, (MULTI || !OBS) ? 4 : 8) env_kern
         }
 
         float* cf_row = (want_cf && emit) ? a.gnn_cf + row * d.m * 3 : nullptr;
-        run_eval<GS, INCR>(d, lits, tt, INCR ? cntw : cnt_store, satw, &misc[0], cf01, stage, cf_row, gid, gt);
+        run_eval<GS, INCR, OBS>(d, lits, tt, INCR ? cntw : cnt_store, satw, &misc[0], cf01, stage, cf_row, pairs, gid, gt);
         group_sync<GS>(gid);
         nunsat = misc[0];
 
@@ -793,7 +876,7 @@ __global__ void __launch_bounds__(kCtaThreads, (MULTI || !OBS) ? 4 : 8) env_kern
                     if (gt == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
                     group_sync<GS>(gid);
                 }
-                run_eval<GS, false>(d, lits, tt, cnt_store, satw, &misc[0], cf01, stage, cf_row, gid, gt);
+                run_eval<GS, false, OBS>(d, lits, tt, cnt_store, satw, &misc[0], cf01, stage, cf_row, pairs, gid, gt);
                 group_sync<GS>(gid);
                 nunsat = misc[0];
                 step_cur = 0;
@@ -925,7 +1008,7 @@ __global__ void __launch_bounds__(128) export_kernel(const Dims d, const ExportA
         for (int c = tid; c < d.m; c += nt) {
             bool sat = false;
             for (int j = 0; j < d.k; ++j) {
-                const uint32_t code = lits[lit_index(d.m, c, j)];
+                const uint32_t code = lits[lit_index(d.ms, c, j)];
                 if (code != lit_pad(d)) {
                     const uint32_t v = code >> 1;
                     sat |= (((st[v >> 5] >> (v & 31)) ^ code) & 1u) != 0u;
@@ -942,7 +1025,7 @@ __global__ void __launch_bounds__(128) export_kernel(const Dims d, const ExportA
         for (int i = tid; i < d.A; i += nt) a.done[(size_t)e * d.A + i] = (uint8_t)(tail[ST_FLAGS] & 1u);
     if (a.clauses || a.l2a)
         for (int i = tid; i < d.m * d.k; i += nt) {
-            const uint32_t code = lits[lit_index(d.m, i / d.k, i % d.k)];
+            const uint32_t code = lits[lit_index(d.ms, i / d.k, i % d.k)];
             const int v = (code == lit_pad(d)) ? -1 : (int)(code >> 1);
             if (a.clauses) a.clauses[(size_t)e * d.m * d.k + i] = v < 0 ? 0 : ((code & 1u) ? -(v + 1) : (v + 1));
             // env:160: index -1 wraps to the last variable
