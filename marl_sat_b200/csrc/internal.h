@@ -16,7 +16,8 @@ constexpr int kMaxSmemOptin = 227 * 1024;
 struct GroupLayout {
     int rec, st, satw, satw_old, x, smx, tt, stage, bar, misc, total;
 };
-constexpr int kCfStageBytes = 12 * 256 + 16;      // clause-feature staging of eval_clauses_gnn (256 clauses per pass)
+constexpr int kCfStageClauses = 256;               // clauses per staging pass of the GNN clause features
+constexpr int kCfStageBytes = 12 * kCfStageClauses + 16;
 inline GroupLayout group_layout(const Dims& d, bool obs) {
     GroupLayout L;
     int o = 0;

@@ -160,7 +160,6 @@ __device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.b
 // memory (lane = clause, three conflict-free 4-byte stores) at the same 16-byte phase as their global
 // destination and leave as ONE bulk (TMA) store per pass; the <= 3 floats before / after the 16-byte
 // aligned body go out as scalars.
-constexpr int kCfStageClauses = 256;
 
 // number of true literals of clause c (lane = clause); K3: three literals per clause, no loop
 template <bool K3>

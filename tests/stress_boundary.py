@@ -18,10 +18,10 @@ def main():
     dev = torch.device("cuda")
     for (n, m, B) in ((100, 430, 65536), (50, 218, 65536), (20, 91, 131072)):
         problems = uniform_ksat_torch(4096, n, m, 3, seed=1, device=dev)
-        for gs in (0, 32, 64, 128, 256):
+        for gs in (0, 16, 32, 64, 128, 256):
             for max_steps in (2, 3, 5):
                 env = M.SATEnv(n, m, max_steps, verbose=False, group_threads=gs)
-                vec = M.VecSATEnv(env, problems, B, M.prng_key(gs + max_steps), emit_obs=(gs in (0, 256)))
+                vec = M.VecSATEnv(env, problems, B, M.prng_key(gs + max_steps), emit_obs=(gs in (0, 16, 256)))
                 vec.reset()
                 g = torch.Generator(device=dev).manual_seed(0)
                 acts = torch.randint(0, env.max_vars_per_agent + 1, (8, B, env.num_agents), generator=g, device=dev,
