@@ -285,18 +285,24 @@ __device__ __forceinline__ void eval_clauses_pairs(const Dims& d, const uint16_t
                 if (gt == 0) tma_store_wait_read();        // the previous pass has left the staging buffer
                 group_sync<GS>(gid);
             }
-            const bool wide = (phase16 & 7u) == 0u;
             const int npass = (c1 - c0 + 1) >> 1;            // pairs of this pass (the last may be half valid)
-            for (int q = gt; q < npass; q += GS) {
-                uint32_t ca, cb;
-                counts((c0 >> 1) + q, ca, cb);
-                const float2 f = cf01[ca], g = cf01[cb];
-                float* o = reinterpret_cast<float*>(stage + phase16 + 24 * q);
-                if (wide) {
-                    reinterpret_cast<float2*>(o)[0] = f;
-                    reinterpret_cast<float2*>(o)[1] = make_float2(1.0f, g.x);
-                    reinterpret_cast<float2*>(o)[2] = make_float2(g.y, 1.0f);
-                } else {
+            const int p0 = c0 >> 1;
+            if ((phase16 & 7u) == 0u) {                      // 8-byte aligned pair slots: three 64-bit stores
+                for (int q = gt; q < npass; q += GS) {
+                    uint32_t ca, cb;
+                    counts(p0 + q, ca, cb);
+                    const float2 f = cf01[ca], g = cf01[cb];
+                    float2* o = reinterpret_cast<float2*>(stage + phase16 + 24 * q);
+                    o[0] = f;
+                    o[1] = make_float2(1.0f, g.x);
+                    o[2] = make_float2(g.y, 1.0f);
+                }
+            } else {
+                for (int q = gt; q < npass; q += GS) {
+                    uint32_t ca, cb;
+                    counts(p0 + q, ca, cb);
+                    const float2 f = cf01[ca], g = cf01[cb];
+                    float* o = reinterpret_cast<float*>(stage + phase16 + 24 * q);
                     o[0] = f.x; o[1] = f.y; o[2] = 1.0f;
                     o[3] = g.x; o[4] = g.y; o[5] = 1.0f;
                 }
@@ -396,13 +402,14 @@ __device__ __forceinline__ void threefry_assign(const Dims& d, uint32_t k0, uint
 }
 
 // Apply all agents' flips simultaneously (env:233-250) on the packed assignment in shared memory.
+// has_pre: the caller already holds act[gt] (mode 0) in `pre` (loaded early, next to the state record).
 template <int GS>
 __device__ __forceinline__ void apply_actions(const Dims& d, const int32_t* __restrict__ actions, int e,
-                                              uint32_t* assign, int gt) {
+                                              uint32_t* assign, int gt, bool has_pre, int pre) {
     if (d.action_mode == 0) {
         const int32_t* act = actions + (size_t)e * d.A;
         for (int a = gt; a < d.A; a += GS) {
-            const int x = act[a];
+            const int x = (has_pre && a == gt) ? pre : act[a];
             const int size = group_size(d, a);
             if (x >= size) continue;                       // env:236 no-op
             int idx = x < size - 1 ? x : size - 1;         // env:238
@@ -698,20 +705,36 @@ __global__ void __launch_bounds__(kCtaThreads, (MULTI || !OBS) ? 4 : 8) env_kern
     float2* cf01 = reinterpret_cast<float2*>(misc + 4);  // {t > 0, t / 3.0} for t = 0..15 true literals (learner:185)
 
     // ---- stage the state record (plain loads) ----
-    if (MODE == MODE_RESET) {
-#pragma unroll 1
-        for (int i = gt; i < d.state_words; i += GS) st[i] = 0u;
-    } else {
-        // state records are multiples of 16 bytes (state_words % 4 == 0) in a 16-byte aligned array
-        const uint4* sin = reinterpret_cast<const uint4*>(a.state_in + (size_t)e * d.state_words);
-#pragma unroll 1
-        for (int i = gt; i < (d.state_words >> 2); i += GS) reinterpret_cast<uint4*>(st)[i] = sin[i];
+    // The two global loads every step waits for -- this lane's piece of the state record and its first action --
+    // are issued back to back before anything consumes them, so their latencies overlap each other and the
+    // shared-memory set-up below instead of adding up.
+    // state records are multiples of 16 bytes (state_words % 4 == 0) in a 16-byte aligned array
+    const uint4* sin = (MODE == MODE_RESET) ? nullptr
+                                            : reinterpret_cast<const uint4*>(a.state_in + (size_t)e * d.state_words);
+    const int sw4 = d.state_words >> 2;
+    uint4 s0 = make_uint4(0u, 0u, 0u, 0u);
+    if (MODE != MODE_RESET && gt < sw4) s0 = sin[gt];
+    if constexpr (GS < 32) {            // issue-bound half-warp groups: no registers to spare for the overlap
+        if (gt < sw4) reinterpret_cast<uint4*>(st)[gt] = s0;
     }
+    int act_pre = 0;
+    const bool act_pre_ok = GS >= 32 && MODE == MODE_STEP && !INCR && d.action_mode == 0 && gt < d.A;
+    if (act_pre_ok) act_pre = a.actions[(size_t)e * d.A + gt];
     if (gt == 0) {
         misc[0] = d.m;              // #unsatisfied accumulator of multi-warp groups: m minus the satisfied counts
         mbar_init(bar, 1);
     }
     if (want_cf && gt < 16) cf01[gt] = make_float2(gt > 0 ? 1.0f : 0.0f, __fdiv_rn((float)gt, 3.0f));
+    if constexpr (GS >= 32) {
+        if (gt < sw4) reinterpret_cast<uint4*>(st)[gt] = s0;
+    }
+    if (MODE != MODE_RESET) {
+#pragma unroll 1
+        for (int i = gt + GS; i < sw4; i += GS) reinterpret_cast<uint4*>(st)[i] = sin[i];
+    } else {
+#pragma unroll 1
+        for (int i = gt + GS; i < sw4; i += GS) reinterpret_cast<uint4*>(st)[i] = make_uint4(0u, 0u, 0u, 0u);
+    }
     group_sync<GS>(gid);
 
     // Every thread keeps its own copy of the scalar state fields in registers from here on: thread 0 rewrites
@@ -764,7 +787,8 @@ __global__ void __launch_bounds__(kCtaThreads, (MULTI || !OBS) ? 4 : 8) env_kern
         } else if (MODE == MODE_STEP) {
             if (INCR) apply_actions_incr<GS>(d, a.actions + (long long)j * a.act_step_stride, e,
                                              a.bank + (size_t)pidx * d.rec_bytes, st, cntw, gt);
-            else apply_actions<GS>(d, a.actions + (long long)j * a.act_step_stride, e, st, gt);
+            else apply_actions<GS>(d, a.actions + (long long)j * a.act_step_stride, e, st, gt,
+                                   act_pre_ok && j == 0, act_pre);
         }
         if (!INCR && cnt_store)
             for (int i = gt; i < d.cnt_words; i += GS) cnt_store[i] = 0u;
