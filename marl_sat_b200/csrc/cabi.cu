@@ -110,9 +110,11 @@ int finish_plan(msat_plan* p) {
         // incremental clause update: var -> clause occurrence lists (CSR) behind the mask stream --
         // u16 row_off[n + 1] (padded to 8 entries), u16 occ[m * k] = (clause << 1) | negated
         d.csr_off = d.rec_copy_bytes;
-        d.rec_bytes = (d.csr_off + 2 * ((n + 1 + 7) & ~7) + 2 * m * k + 127) & ~127;
+        d.csr_bytes = (2 * ((n + 1 + 7) & ~7) + 2 * m * k + 15) & ~15;
+        d.rec_bytes = (d.csr_off + d.csr_bytes + 127) & ~127;
     } else {
         d.csr_off = 0;
+        d.csr_bytes = 0;
         d.rec_bytes = (d.rec_copy_bytes + 127) & ~127;
     }
     d.state_words = (d.aw + 4 + d.cnt_words + 3) & ~3;

@@ -16,6 +16,7 @@ struct Dims {
     int rec_bytes;        // bank record size = stride between records (multiple of 128)
     int rec_copy_bytes;   // leading part staged by observation-writing launches: literals + agent-mask stream
     int csr_off;          // byte offset of the var -> clause occurrence lists inside a record (0 = not built)
+    int csr_bytes;        // their size, padded to 16 bytes (one TMA bulk copy into the group's record slot)
     int cnt_words;        // incremental clause update: words of per-clause true-literal counts (4 bits each) in the
                           // state record after the 4 scalar fields; 0 = full recompute (default)
     int state_words;      // env-state record words (multiple of 4)

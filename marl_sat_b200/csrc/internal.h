@@ -21,7 +21,10 @@ constexpr int kCfStageBytes = 12 * kCfStageClauses + 16;
 inline GroupLayout group_layout(const Dims& d, bool obs) {
     GroupLayout L;
     int o = 0;
-    L.rec = o;  o += ((obs ? d.rec_copy_bytes : d.lits_bytes) + 127) & ~127;   // TMA destination, 128-byte aligned
+    // TMA destination, 128-byte aligned: whole record (observations), literal block, or -- in the step launches of
+    // an incremental plan -- the occurrence lists, whichever is larger
+    const int noobs_rec = d.lits_bytes > d.csr_bytes ? d.lits_bytes : d.csr_bytes;
+    L.rec = o;  o += ((obs ? d.rec_copy_bytes : noobs_rec) + 127) & ~127;
     L.st = o;   o += 4 * d.state_words;           // state record (multiple of 16 bytes)
     L.stage = o; o += obs ? 0 : kCfStageBytes;    // 16-byte aligned (rec and state sizes are multiples of 16)
     L.satw = o; o += 4 * d.sw;

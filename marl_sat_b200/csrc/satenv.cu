@@ -432,13 +432,13 @@ __device__ __forceinline__ void apply_actions(const Dims& d, const int32_t* __re
 }
 
 // Incremental clause update (env:130-156 restricted to the clauses adjacent to the flipped variables): every
-// flipping (agent, variable) walks the variable's occurrence list in the bank record (global memory, read
-// once) and moves the 4-bit true-literal count of each adjacent clause by +-1.  A variable flips at most
+// flipping (agent, variable) walks the variable's occurrence list -- staged in shared memory by a TMA bulk copy
+// of the record's CSR block -- and moves the 4-bit true-literal count of each adjacent clause by +-1.  A variable flips at most
 // once per step (agents own disjoint variables), so its new value is the old one inverted; the partial sums
 // of a clause's updates stay within [0, k] in any order, so the packed nibbles never carry or borrow.
-__device__ __forceinline__ void flip_and_update_counts(const Dims& d, const uint8_t* __restrict__ rec_g, int v,
+__device__ __forceinline__ void flip_and_update_counts(const Dims& d, const uint8_t* csr, int v,
                                                        uint32_t* assign, uint32_t* cntw) {
-    const uint16_t* row_off = reinterpret_cast<const uint16_t*>(rec_g + d.csr_off);
+    const uint16_t* row_off = reinterpret_cast<const uint16_t*>(csr);
     const uint16_t* occ = row_off + ((d.n + 1 + 7) & ~7);
     const uint32_t bit = 1u << (v & 31);
     const uint32_t now_true = ((assign[v >> 5] & bit) == 0u) ? 1u : 0u;      // value after the flip
@@ -455,7 +455,7 @@ __device__ __forceinline__ void flip_and_update_counts(const Dims& d, const uint
 
 template <int GS>
 __device__ __forceinline__ void apply_actions_incr(const Dims& d, const int32_t* __restrict__ actions, int e,
-                                                   const uint8_t* __restrict__ rec_g, uint32_t* assign, uint32_t* cntw,
+                                                   const uint8_t* csr, uint32_t* assign, uint32_t* cntw,
                                                    int gt) {
     if (d.action_mode == 0) {
         const int32_t* act = actions + (size_t)e * d.A;
@@ -467,14 +467,14 @@ __device__ __forceinline__ void apply_actions_incr(const Dims& d, const int32_t*
             if (idx < 0) idx += d.V;                       // JAX gather: wrap once, then clamp
             idx = idx < 0 ? 0 : (idx > d.V - 1 ? d.V - 1 : idx);
             if (idx >= size) continue;                     // landed on a -1 pad: one_hot(-1) = 0 (env:243)
-            flip_and_update_counts(d, rec_g, group_start(d, a) + idx, assign, cntw);
+            flip_and_update_counts(d, csr, group_start(d, a) + idx, assign, cntw);
         }
     } else {
         const int32_t* act = actions + (size_t)e * d.A * d.V;
         for (int i = gt; i < d.A * d.V; i += GS) {
             const int a = i / d.V, j = i - a * d.V;
             if (j < group_size(d, a) && (act[i] & 1))      // env:246-250 (actions are 0/1)
-                flip_and_update_counts(d, rec_g, group_start(d, a) + j, assign, cntw);
+                flip_and_update_counts(d, csr, group_start(d, a) + j, assign, cntw);
         }
     }
 }
@@ -747,7 +747,8 @@ __global__ void __launch_bounds__(kCtaThreads, (MULTI || !OBS) ? 4 : 8) env_kern
     if (MODE == MODE_RESET) pidx = a.prob_idx[e];
     else pidx = (int)st_tail[ST_PIDX];
     pidx = pidx < 0 ? 0 : (pidx >= a.P ? a.P - 1 : pidx);
-    int loaded_pidx = -1;
+    int loaded_pidx = -1;           // formula whose block sits in the record slot ...
+    bool loaded_csr = false;        // ... and whether that block is its occurrence lists (incremental steps) or its literals
     uint32_t phase = 0u;
     int nunsat = nunsat_prev;
 
@@ -763,6 +764,14 @@ __global__ void __launch_bounds__(kCtaThreads, (MULTI || !OBS) ? 4 : 8) env_kern
             if (j > 0) fence_proxy_async();
             mbar_expect_tx(bar, tma_bytes);
             tma_load_1d(rec, a.bank + (size_t)pidx * d.rec_bytes, tma_bytes, bar);
+        }
+        // incremental step: the var -> clause occurrence lists of the formula instead (the literals are needed
+        // only when the episode restarts)
+        const bool need_csr = INCR && !(loaded_csr && loaded_pidx == pidx);
+        if (need_csr && gt == 0) {
+            if (j > 0) fence_proxy_async();
+            mbar_expect_tx(bar, (uint32_t)d.csr_bytes);
+            tma_load_1d(rec, a.bank + (size_t)pidx * d.rec_bytes + d.csr_off, (uint32_t)d.csr_bytes, bar);
         }
         if (MODE == MODE_STEP && a.reward_mode) {
             // shaped reward (env:201-223): clause status of the state BEFORE the flips
@@ -785,8 +794,15 @@ __global__ void __launch_bounds__(kCtaThreads, (MULTI || !OBS) ? 4 : 8) env_kern
         if (MODE == MODE_RESET) {
             threefry_assign<GS>(d, a.keys[2 * (size_t)e], a.keys[2 * (size_t)e + 1], st, gt);
         } else if (MODE == MODE_STEP) {
-            if (INCR) apply_actions_incr<GS>(d, a.actions + (long long)j * a.act_step_stride, e,
-                                             a.bank + (size_t)pidx * d.rec_bytes, st, cntw, gt);
+            if (INCR) {
+                if (need_csr) {
+                    mbar_wait(bar, phase);
+                    phase ^= 1u;
+                    loaded_pidx = pidx;
+                    loaded_csr = true;
+                }
+                apply_actions_incr<GS>(d, a.actions + (long long)j * a.act_step_stride, e, rec, st, cntw, gt);
+            }
             else apply_actions<GS>(d, a.actions + (long long)j * a.act_step_stride, e, st, gt,
                                    act_pre_ok && j == 0, act_pre);
         }
@@ -871,10 +887,13 @@ __global__ void __launch_bounds__(kCtaThreads, (MULTI || !OBS) ? 4 : 8) env_kern
                     rk1 = a.keys[2 * (size_t)e + 1];
                 }
                 pidx = pidx < 0 ? 0 : (pidx >= a.P ? a.P - 1 : pidx);
+                // the full evaluation of the new episode needs the literal block (an incremental step had the
+                // occurrence lists in the slot)
+                const bool need_lits = pidx != loaded_pidx || (INCR && loaded_csr);
                 if (gt == 0) {
                     misc[0] = d.m;
                     if (a.reset_count) atomicAdd(a.reset_count, 1ULL);
-                    if (pidx != loaded_pidx) {
+                    if (need_lits) {
                         fence_proxy_async();
                         mbar_expect_tx(bar, tma_bytes);
                         tma_load_1d(rec, a.bank + (size_t)pidx * d.rec_bytes, tma_bytes, bar);
@@ -887,10 +906,11 @@ __global__ void __launch_bounds__(kCtaThreads, (MULTI || !OBS) ? 4 : 8) env_kern
                 threefry_assign<GS>(d, rk0, rk1, st, gt);
                 group_sync<GS>(gid);
                 build_truth_table<GS>(d, st, tt, gt);
-                if (pidx != loaded_pidx) {
+                if (need_lits) {
                     mbar_wait(bar, phase);
                     phase ^= 1u;
                     loaded_pidx = pidx;
+                    loaded_csr = false;
                 }
                 group_sync<GS>(gid);
                 // the clause features of the finished episode are already on their way to the same rows: let
