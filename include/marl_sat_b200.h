@@ -248,9 +248,10 @@ int msat_shutdown(void);
  * rec_bytes and state_words change with the mode (re-read them with msat_plan_dims).
  *   MSAT_CLAUSES_FULL (default)   every step re-evaluates all m clauses from the staged literal block;
  *   MSAT_CLAUSES_INCREMENTAL      the state carries a 4-bit true-literal count per clause and the bank
- *        record the var -> clause occurrence lists (CSR); a step touches only the clauses adjacent to the
- *        flipped variables (env:130-156 restricted to those clauses) and never reads the literal block unless
- *        the episode restarts.  Needs lits_per_clause <= 15.  Results are bit-identical in both modes;
+ *        record the var -> clause occurrence lists (CSR); a step stages the CSR block (not the literal block) in
+ *        shared memory with one TMA bulk copy, touches only the clauses adjacent to the flipped variables
+ *        (env:130-156 restricted to those clauses) and reads the literals only when the episode restarts.
+ *        Needs lits_per_clause <= 15.  Results are bit-identical in both modes;
  *        launches that do write observations keep the counts up to date with a full evaluation. */
 #define MSAT_CLAUSES_FULL        0
 #define MSAT_CLAUSES_INCREMENTAL 1

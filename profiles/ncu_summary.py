@@ -14,7 +14,8 @@ cols = [("gpu__time_duration.sum", "time"), ("dram__bytes_read.sum", "dram_rd"),
         ("launch__shared_mem_per_block_dynamic", "dsmem"),
         ("l1tex__data_pipe_lsu_wavefronts_mem_shared.sum.pct_of_peak_sustained_elapsed", "smem%"),
         ("lts__t_sector_hit_rate.pct", "l2hit%")]
-print("kernel," + ",".join(f"{n}[{units[idx[m]]}]" for m, n in cols if m in idx))
+w = csv.writer(sys.stdout)          # kernel names contain commas: quoted
+w.writerow(["kernel"] + [f"{n}[{units[idx[m]]}]" for m, n in cols if m in idx])
 for r in data:
     name = r[idx["Kernel Name"]].split("(")[0].replace("void ", "")
-    print(name + "," + ",".join(r[idx[m]] for m, n in cols if m in idx))
+    w.writerow([name] + [r[idx[m]] for m, n in cols if m in idx])
