@@ -66,7 +66,7 @@ typedef struct msat_dims {
 /* Replaces SATEnv.__init__/_create_agent_groups (env:29-88, 294-338).
  * `num_agents` is the value produced by the reference's grouping rule; the
  * contiguous split base=n/A, rem=n%A is implied.  group_threads = 0 lets the
- * library choose (32/64/128/256 by observation size). */
+ * library choose (16/32/64/128/256 by observation size; 16 = two envs share a warp). */
 int msat_plan_create(msat_plan** out, int32_t num_vars, int32_t num_clauses, int32_t lits_per_clause,
                      int32_t num_agents, int32_t action_mode, int32_t max_steps, int32_t group_threads);
 void msat_plan_destroy(msat_plan* plan);

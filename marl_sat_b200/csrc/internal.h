@@ -44,7 +44,7 @@ inline GroupLayout group_layout(const Dims& d, bool obs) {
 
 struct msat_plan {
     msat::Dims d;
-    int group_threads;     // GS: threads cooperating on one env (32/64/128/256)
+    int group_threads;     // GS: threads cooperating on one env (16 = two envs per warp, 32/64/128/256)
     int group_smem_bytes;  // shared memory per env group (multiple of 128)
     int smem_bytes;        // dynamic shared memory per 256-thread CTA
     int group_threads_noobs;   // GS used when a launch writes no observations (little per-env work: small groups)

@@ -646,9 +646,12 @@ __device__ __forceinline__ void rng_advance(uint32_t& r0, uint32_t& r1) {
 }
 
 // =====================================================================================
-// K_env<GS, MODE, OBS>: reset / step (+ fused auto-reset, + K fused steps) / get_obs.
-// 256-thread CTAs, 256/GS envs each.  OBS = the launch writes local observations (whole bank record
-// staged, observation re-basing buffers); !OBS = literal block only, optional GNN-input outputs.
+// K_env<GS, MODE, OBS, MULTI, INCR>: reset / step (+ fused auto-reset, + K fused steps) / get_obs.
+// 256-thread CTAs, 256/GS envs each (GS = 16: two envs per warp, observation-writing launches only).
+// OBS = the launch writes local observations (whole bank record staged, observation re-basing buffers);
+// !OBS = literal block only (or, INCR, the CSR occurrence lists), optional GNN-input outputs.
+// MULTI = K steps per launch (msat_rollout_steps); INCR = incremental clause update (step launches of a plan
+// with MSAT_CLAUSES_INCREMENTAL that write no observations).
 // =====================================================================================
 template <int GS, int MODE, bool OBS, bool MULTI, bool INCR>
 __global__ void __launch_bounds__(kCtaThreads, (MULTI || !OBS) ? 4 : 8) env_kernel(const Dims d, const EnvArgs a) {

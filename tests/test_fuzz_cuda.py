@@ -139,16 +139,22 @@ def test_timeout_boundary_stress(gs):
     torch.cuda.synchronize()
 
 
+@pytest.mark.parametrize("variant", ["incremental", "full_k3"])
 @pytest.mark.parametrize("seed", range(16))
-def test_incremental_clause_update_without_observations(seed):
-    """The incremental (CSR occurrence-list) update only runs in launches that write no observations: rollouts
-    through ``emit_obs=False`` / ``gnn_outputs=True`` -- single steps and K fused steps, interleaved with
-    observation-writing launches on the same state -- against the oracle, on unstructured formulas (repeated
-    variables, x and -x in one clause, 0 padding anywhere), both action modes, every group size."""
+def test_incremental_clause_update_without_observations(seed, variant):
+    """The launches that write no observations have their own clause evaluators: the incremental (CSR
+    occurrence-list) update (``variant == "incremental"``) and, for k = 3 with the full recompute, the paired
+    evaluator (two adjacent clauses per lane, no status words; ``variant == "full_k3"``: odd and even m, more than
+    one 256-clause staging pass, every 16-byte phase of the feature rows).  Rollouts through ``emit_obs=False`` /
+    ``gnn_outputs=True`` -- single steps and K fused steps, interleaved with observation-writing launches on the
+    same state -- against the oracle, on unstructured formulas (repeated variables, x and -x in one clause, 0
+    padding anywhere), both action modes, every group size."""
     import marl_sat_b200 as M
     from oracle import features as ofeat
     rng = np.random.default_rng(4000 + seed)
     n, m, k = int(rng.integers(2, 70)), int(rng.integers(1, 300)), int(rng.integers(1, 8))
+    if variant == "full_k3":
+        m, k = int(rng.integers(1, 700)), 3
     vpa = [None, 1, 3, 5, 7][seed % 5]
     if vpa is not None and vpa > n:
         vpa = n
@@ -159,7 +165,7 @@ def test_incremental_clause_update_without_observations(seed):
     problems = _random_formulas(rng, P, n, m, k)
     ref = SATEnvOracle(n, m, max_steps, vars_per_agent=vpa, action_mode=mode)
     env = M.SATEnv(n, m, max_steps, vars_per_agent=vpa, action_mode=mode, verbose=False, group_threads=gs,
-                   clause_update="incremental")
+                   clause_update="incremental" if variant == "incremental" else "full")
     key0 = otf.prng_key(seed)
     gnn = seed % 3 != 0
     vec = M.VecSATEnv(env, problems, B, key0, emit_obs=False, gnn_outputs=gnn)
