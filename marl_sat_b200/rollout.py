@@ -328,18 +328,28 @@ class VecSATEnv:
         action upload, the fused step and the result download of this call overlap the neighbouring steps'.
         ``actions_host`` (pinned; default ``slot['host']['actions']``) must stay untouched until the step's
         kernel has run; read the results from ``slot['host']`` after ``host_wait(slot_idx)``."""
-        host, out, dev = slot["host"], slot["dev"], self.state.device
+        host, dev = slot["host"], self.state.device
         acts = host["actions"] if actions_host is None else actions_host
         k, cur = self.keys, self.keys._cur
-        done, reward = out["done"], out["reward"]
-        rc = self.env._lib.msat_rollout_step_host_async(
-            self._pipe, slot_idx, self.bank.plan.handle, _ptr(self.bank.data), self.bank.num_problems,
-            _ptr(self.state), acts.data_ptr(), slot["actions_dev"].data_ptr(), _ptr(k._bufs[cur]),
-            _ptr(k._bufs[1 - cur]), self.num_envs_global, self.env_offset, _ptr(out["obs"]), _ptr(reward),
-            int(reward.shape[-1]), _ptr(done), int(done.shape[-1]), _ptr(out["solved"]),
-            _ptr(out["num_unsatisfied"]), _ptr(out["episode_step"]), _ptr(host["reward"]), _ptr(host["done"]),
-            _ptr(host["solved"]), _ptr(host["num_unsatisfied"]), _ptr(host["episode_step"]), self.num_envs,
-            torch.cuda.current_stream(dev).cuda_stream)
+        fixed = slot.get("_bound")
+        if fixed is None:
+            # the argument list of this slot, bound once (every buffer of a slot is fixed); per call only the
+            # action pointer, the two rng buffers and the stream change
+            out = slot["dev"]
+            done, reward = out["done"], out["reward"]
+            fixed = slot["_bound"] = [
+                self._pipe, int(slot_idx), self.bank.plan.handle, _ptr(self.bank.data), self.bank.num_problems,
+                _ptr(self.state), None, slot["actions_dev"].data_ptr(), None, None, self.num_envs_global,
+                self.env_offset, _ptr(out["obs"]), _ptr(reward), int(reward.shape[-1]), _ptr(done),
+                int(done.shape[-1]), _ptr(out["solved"]), _ptr(out["num_unsatisfied"]), _ptr(out["episode_step"]),
+                _ptr(host["reward"]), _ptr(host["done"]), _ptr(host["solved"]), _ptr(host["num_unsatisfied"]),
+                _ptr(host["episode_step"]), self.num_envs, None]
+            slot["_chains"] = (_ptr(k._bufs[0]), _ptr(k._bufs[1]))
+        chains = slot["_chains"]
+        fixed[6] = acts.data_ptr()
+        fixed[8], fixed[9] = chains[cur], chains[1 - cur]
+        fixed[26] = torch.cuda.current_stream(dev).cuda_stream
+        rc = self.env._lib.msat_rollout_step_host_async(*fixed)
         if rc != 0:
             _lib.check(rc, "msat_rollout_step_host_async")
         self.keys._cur = 1 - cur
