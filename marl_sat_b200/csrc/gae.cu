@@ -111,7 +111,6 @@ __global__ void __launch_bounds__(32 * S) gae_kernel(const float* __restrict__ r
 // GP_CH time steps per warp keeps ~27 KB per warp in flight without holding registers.  Four independent
 // recurrences per lane give the instruction-level parallelism that the lower warp count takes away.  No
 // cross-warp synchronisation; per column the arithmetic (and its rounding order) is gae_segment's.
-constexpr int GP_COLS = 128;                // columns per warp (4 per lane)
 int g_gae_variant = 0;                      // msat_tune("gae_variant", 4 | 2 | 1): pin the columns per lane (sweeps)
 int g_gae_pipe_min_cols = 24576;            // smallest batch that takes the pipelined scan; msat_tune("gae_pipe_min_cols", B)
 
