@@ -607,32 +607,24 @@ def main_ours(args):
         norm_once()
         torch.cuda.synchronize()
         g0, g1, g2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
-        if world == 1:
-            # replayed as CUDA graphs of `reps` launches each: the ~100 us / ~40 us kernels are timed without the
-            # Python wrapper's per-call work
-            gs_, gn_ = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
-            with torch.cuda.graph(gs_):
-                for _ in range(reps):
-                    scan_once()
-            with torch.cuda.graph(gn_):
-                for _ in range(reps):
-                    norm_once()
-            gs_.replay()                    # first replay uploads the graph: untimed
-            gn_.replay()
-            torch.cuda.synchronize()
-            g0.record()
-            gs_.replay()
-            g1.record()
-            gn_.replay()
-            g2.record()
-        else:
-            g0.record()
+        # replayed as CUDA graphs of `reps` launches each: the ~100 us / ~40 us kernels (10-30 us on the shards of a
+        # multi-GPU run) are timed without the Python wrapper's per-call work; no collective is captured (the
+        # statistics all-reduce is timed separately above)
+        gs_, gn_ = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
+        with torch.cuda.graph(gs_):
             for _ in range(reps):
                 scan_once()
-            g1.record()
+        with torch.cuda.graph(gn_):
             for _ in range(reps):
                 norm_once()
-            g2.record()
+        gs_.replay()                    # first replay uploads the graph: untimed
+        gn_.replay()
+        torch.cuda.synchronize()
+        g0.record()
+        gs_.replay()
+        g1.record()
+        gn_.replay()
+        g2.record()
         torch.cuda.synchronize()
         scan_ms, norm_ms = g0.elapsed_time(g1) / reps, g1.elapsed_time(g2) / reps
         gae_info = {"num_steps": T, "num_envs": B, "scan_ms": scan_ms, "normalize_ms": norm_ms,

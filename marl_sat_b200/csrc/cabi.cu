@@ -235,6 +235,7 @@ int msat_tune(const char* key, int32_t value) {
     if (!strcmp(key, "gae_plain")) { g_gae_force_plain = value; return MSAT_OK; }
     if (!strcmp(key, "gae_variant")) { g_gae_variant = value; return MSAT_OK; }
     if (!strcmp(key, "gae_pipe_min_cols")) { g_gae_pipe_min_cols = value; return MSAT_OK; }
+    if (!strcmp(key, "gae_warps_per_sm")) { g_gae_warps_per_sm = value > 0 ? value : 0; return MSAT_OK; }
     return MSAT_EINVAL;
 }
 

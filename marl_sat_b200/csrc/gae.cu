@@ -112,6 +112,7 @@ __global__ void __launch_bounds__(32 * S) gae_kernel(const float* __restrict__ r
 // recurrences per lane give the instruction-level parallelism that the lower warp count takes away.  No
 // cross-warp synchronisation; per column the arithmetic (and its rounding order) is gae_segment's.
 int g_gae_variant = 0;                      // msat_tune("gae_variant", 4 | 2 | 1): pin the columns per lane (sweeps)
+int g_gae_warps_per_sm = 0;                // segmented scan: split time until this many warps per SM (0 = by batch); msat_tune("gae_warps_per_sm", w)
 int g_gae_pipe_min_cols = 24576;            // smallest batch that takes the pipelined scan; msat_tune("gae_pipe_min_cols", B)
 
 __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
@@ -353,7 +354,9 @@ cudaError_t launch_gae(const float* reward, long long rs_t, long long rs_b, cons
     const int grid = (B + 31) / 32;
     // enough warps to cover HBM latency: >= 8 per SM, segments of at least one load chunk
     int S = 1;
-    while (S < 32 && grid * S < 148 * 8 && T / (2 * S) >= GAE_CHUNK) S *= 2;
+    // measured (profiles/r2_gae_sweep.txt, "segments"): 8 warps per SM up to 8,192 columns, 16 above
+    const int wps = g_gae_warps_per_sm > 0 ? g_gae_warps_per_sm : (grid > 256 ? 16 : 8);
+    while (S < 32 && grid * S < 148 * wps && T / (2 * S) >= GAE_CHUNK) S *= 2;
     const int seg_len = (T + S - 1) / S;
     // the batch fills the GPU by itself and the rows are 16-byte copyable: pipelined plain scan
     const bool rows16 = rs_b == 1 && (rs_t % 4) == 0 && (B % 4) == 0 &&

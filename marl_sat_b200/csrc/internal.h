@@ -107,6 +107,7 @@ enum EnvMode { MODE_RESET = 0, MODE_STEP = 1, MODE_OBS = 2 };
 extern int g_gae_force_plain;   // gae.cu; msat_tune("gae_plain", 1)
 extern int g_gae_variant;       // gae.cu; msat_tune("gae_variant", v)
 extern int g_gae_pipe_min_cols; // gae.cu; msat_tune("gae_pipe_min_cols", B)
+extern int g_gae_warps_per_sm;  // gae.cu; msat_tune("gae_warps_per_sm", w)
 
 struct ExportArgs {
     const uint8_t* bank;
