@@ -730,6 +730,30 @@ def main_ours(args):
             del bank_i, env_i
         except torch.OutOfMemoryError:
             pass
+    # ---- extra: the same step with int8 observations (MSAT_OBS_INT8): same values, a quarter of the bytes --------
+    # for consumers that cast the observations anyway; the headline metric above is always the int32 contract.
+    i8_info = None
+    if world == 1 and not args.no_gnn_leg:
+        env8 = M.SATEnv(w["n"], w["m"], MAX_STEPS, vars_per_agent=w["vpa"], verbose=False, device=dev,
+                        group_threads=args.group_threads, obs_dtype=torch.int8)
+        vec8 = M.VecSATEnv(env8, bank.for_env(env8), Bg, M.prng_key(SEED + 4))
+        vec8.reset()
+        dephase(vec8)
+        for i in range(5):
+            vec8.step(actions[i])
+        torch.cuda.synchronize()
+        K8 = min(K, 100)
+        i8_ms = _time_steps(torch, lambda i: vec8.step(actions[i % ACTION_CYCLE]), K8) / K8
+        d8 = bank.plan.dims
+        copy_bytes = (w["m"] * w["k"] * 2 + 15) // 16 * 16 + 4 * ((A * env.obs_dim + 31) // 32 + 1)
+        i8_bytes = A * env.obs_dim + copy_bytes + 2 * 4 * d8.state_words + 4 * A + 4 * A + (A + 1) + 9 + 12
+        i8_info = {"value": Bg / (i8_ms * 1e-3), "unit": UNIT, "ms_per_step": i8_ms, "steps": K8,
+                   "bytes_moved_per_env_step": i8_bytes, "gbs": i8_bytes * B / (i8_ms * 1e-3) / 1e9,
+                   "what": "msat_rollout_step on a plan with msat_plan_set_obs_dtype(MSAT_OBS_INT8): observations "
+                           "int8[B,A,D] with the same -1/0/1 values (parity: tests/test_round2_cuda.py); bytes_moved = "
+                           "int8 observations + staged bank record (packed literals + agent-mask stream) + state r/w "
+                           "+ actions + reward/done/info"}
+        del vec8, env8
     env.count_resets(w["k"], None)
 
     # ---- reduce over ranks (max time) ------------------------------------------------------------------
@@ -827,6 +851,9 @@ def main_ours(args):
         if gnn_info:
             gnn_info["frac_of_hbm_peak"] = gnn_info["gbs"] / peak
             line["gnn_input_mode"] = gnn_info
+        if i8_info:
+            i8_info["frac_of_hbm_peak"] = i8_info["gbs"] / peak
+            line["obs_int8_mode"] = i8_info
         if gae_info:
             gae_info["scan_ms"], gae_info["normalize_ms"] = scan_ms_max, norm_ms_max
             gae_info["scan_gbs"] = 17.0 * gae_info["num_steps"] * B / (scan_ms_max * 1e-3) / 1e9

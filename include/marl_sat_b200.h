@@ -257,6 +257,16 @@ int msat_shutdown(void);
 #define MSAT_CLAUSES_INCREMENTAL 1
 int msat_plan_set_clause_update(msat_plan* plan, int32_t mode);
 
+/* Element type of the observations written by every entry point that uses this plan (call before the first
+ * launch).  The reference declares int32 (env:390-396) and that is the default and the drop-in contract;
+ * values are only ever -1 / 0 / 1, so a consumer that casts them anyway (an MLP's first layer) can ask for
+ *   MSAT_OBS_INT8   the same values as int8: `obs` arguments then point to int8 [.., A, D] (still 16-byte
+ *                   aligned) and the step moves a quarter of the observation bytes.
+ * Not offered through the XLA FFI handlers (their observation buffers are typed S32). */
+#define MSAT_OBS_INT32 0
+#define MSAT_OBS_INT8  1
+int msat_plan_set_obs_dtype(msat_plan* plan, int32_t dtype);
+
 /* Diagnostics: while `counter_dev` (a device uint64, 8-byte aligned, owned by the caller) is set, every
  * auto-reset performed by a step launch that uses this plan adds 1 to it.  NULL switches it off. */
 int msat_plan_set_reset_counter(msat_plan* plan, uint64_t* counter_dev);

@@ -45,6 +45,7 @@ SIGNATURES = {
     "msat_tune": (C.c_int, [C.c_char_p, _i32]),
     "msat_plan_set_reset_counter": (C.c_int, [_p, _p]),
     "msat_plan_set_clause_update": (C.c_int, [_p, _i32]),
+    "msat_plan_set_obs_dtype": (C.c_int, [_p, _i32]),
     "msat_step": (C.c_int, [_p, _p, _i32, _p, _p, _p, _i32, _p, _p, _p, _p, _i32, _p, _i32, _p, _p, _p, _p, _i32, _p]),
     "msat_rollout_steps": (C.c_int, [_p, _p, _i32, _p, _p, _p, _i32, _p, _p, _i32, _i32, _p, _p, _p, _i32, _p, _i32,
                                      _p, _i32, _p, _p, _p, _p, _i32, _p]),

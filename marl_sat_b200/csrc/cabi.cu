@@ -211,6 +211,12 @@ int msat_plan_set_reward(msat_plan* plan, int32_t mode, double gamma, double r_c
     return MSAT_OK;
 }
 
+int msat_plan_set_obs_dtype(msat_plan* plan, int32_t dtype) {
+    if (!plan || (dtype != MSAT_OBS_INT32 && dtype != MSAT_OBS_INT8)) return MSAT_EINVAL;
+    plan->obs_i8 = dtype == MSAT_OBS_INT8;
+    return MSAT_OK;
+}
+
 int msat_plan_set_clause_update(msat_plan* plan, int32_t mode) {
     if (!plan || (mode != MSAT_CLAUSES_FULL && mode != MSAT_CLAUSES_INCREMENTAL)) return MSAT_EINVAL;
     if (mode == MSAT_CLAUSES_INCREMENTAL && plan->d.k > 15) return MSAT_EUNSUPPORTED;     // 4-bit counts

@@ -55,6 +55,7 @@ struct msat_plan {
     int reward_mode = 0;       // MSAT_REWARD_SPARSE / MSAT_REWARD_SHAPED (msat_plan_set_reward)
     float r_gamma = 0.99f, r_clause = 0.02f, r_sat = 1.0f;
     unsigned long long* reset_counter = nullptr;   // device counter of auto-resets (diagnostics), or null
+    int obs_i8 = 0;            // MSAT_OBS_INT8: observations are written as int8 instead of int32
     // devices on which the > 48 KB dynamic shared memory opt-in of the env kernels has been made (bit = device
     // ordinal); set once per (plan, device) instead of once per launch
     mutable std::atomic<unsigned long long> prepared_devices{0};
@@ -100,6 +101,7 @@ struct EnvArgs {
     float r_gamma, r_clause, r_sat;
     int32_t* newly_sat;         // optional int32[(K,) B]: clauses satisfied now that were not before the step
     unsigned long long* reset_count;   // optional device counter: += 1 for every auto-reset (msat_plan_set_reset_counter)
+    int obs_i8;                 // `obs` points to int8 elements (msat_plan_set_obs_dtype)
 };
 
 enum EnvMode { MODE_RESET = 0, MODE_STEP = 1, MODE_OBS = 2 };

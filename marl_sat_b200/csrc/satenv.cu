@@ -540,7 +540,16 @@ __device__ __forceinline__ int4 expand_nibble(uint32_t mn, uint32_t xn) {
 // [B,A,D] tensor.  out[i] = mask[i] ? value[i] : -1 where mask is the bank's flat bit stream and
 // value is [assign | clause status | assign] repeated per agent.  Both streams are re-based to the
 // 128-byte aligned start of the range so every lane owns whole 16-byte chunks (st.global.cs.v4).
-template <int GS>
+// Four observation BYTES (int8) of a mask / value nibble pair: mask ? value : -1 (0xFF).
+__device__ __forceinline__ uint32_t expand_nibble_i8(uint32_t mn, uint32_t xn) {
+    const uint32_t m4 = (mn * 0x00204081u) & 0x01010101u;
+    return ((xn * 0x00204081u) & 0x01010101u) | (0xFFFFFFFFu - m4 * 0xFFu);
+}
+
+// I8 (msat_plan_set_obs_dtype): the same flat range with one byte per element -- `obs` then points to int8 data,
+// a 16-byte chunk covers 16 elements (half a mask / value word pair) and at most 15 bytes at each end of an
+// env's range go out as scalar byte stores.
+template <int GS, bool I8>
 __device__ __forceinline__ void emit_obs(const Dims& d, long long row, const uint32_t* assign, const uint32_t* satw,
                                          uint32_t* X, uint2* smx, const uint32_t* mflat,
                                          int32_t* __restrict__ obs, int gid, int gt) {
@@ -588,6 +597,37 @@ __device__ __forceinline__ void emit_obs(const Dims& d, long long row, const uin
     }
     group_sync<GS>(gid);
 
+    if constexpr (I8) {
+        // ---- int8: chunk q covers elements [16q, 16q+16) of the re-based range (32-byte aligned base) ----
+        int8_t* out8 = reinterpret_cast<int8_t*>(obs) + (g_start - s);
+        const int lo = s, hi = s + d.AD;
+        const int q_lo = (lo + 15) >> 4, q_hi = hi >> 4;
+        {
+            int q = q_lo + gt;                      // GS is even: a lane keeps the same half of its word pair
+            const int sh = (q & 1) * 16;
+            const uint2* sp = smx + (q >> 1);
+            uint4* op = reinterpret_cast<uint4*>(out8) + q;
+#pragma unroll 2
+            for (; q < q_hi; q += GS, sp += GS / 2, op += GS) {
+                const uint2 mx = *sp;
+                const uint32_t m16 = mx.x >> sh, x16 = mx.y >> sh;
+                __stcs(op, make_uint4(expand_nibble_i8(m16 & 0xFu, x16 & 0xFu),
+                                      expand_nibble_i8((m16 >> 4) & 0xFu, (x16 >> 4) & 0xFu),
+                                      expand_nibble_i8((m16 >> 8) & 0xFu, (x16 >> 8) & 0xFu),
+                                      expand_nibble_i8((m16 >> 12) & 0xFu, (x16 >> 12) & 0xFu)));
+            }
+        }
+        // the < 16 elements before the first / after the last complete chunk (or the whole range when it is short)
+        const int head_end = min(16 * q_lo, hi);
+        const int tail_start = max(16 * q_hi, head_end);
+        auto put = [&](int i) {
+            const uint2 mx = smx[i >> 5];
+            out8[i] = ((mx.x >> (i & 31)) & 1u) ? (int8_t)((mx.y >> (i & 31)) & 1u) : (int8_t)-1;
+        };
+        for (int i = lo + gt; i < head_end; i += GS) put(i);
+        for (int i = tail_start + gt; i < hi; i += GS) put(i);
+        return;
+    }
     // ---- streaming stores: chunk q covers ints [4q, 4q+4) of the re-based range ----
     int32_t* out = obs + (g_start - s);
     const int lo_valid = s, hi_valid = s + d.AD;
@@ -975,7 +1015,10 @@ __global__ void __launch_bounds__(kCtaThreads, (MULTI || !OBS) ? 4 : 8) env_kern
         }
         if (emit) {
             if (!OBS && a.gnn_assign) emit_gnn_assignment<GS>(d, row, st, a.gnn_assign, gt);
-            if (OBS && a.obs) emit_obs<GS>(d, row, st, satw, X, smx, mflat, a.obs, gid, gt);
+            if (OBS && a.obs) {
+                if (a.obs_i8) emit_obs<GS, true>(d, row, st, satw, X, smx, mflat, a.obs, gid, gt);
+                else emit_obs<GS, false>(d, row, st, satw, X, smx, mflat, a.obs, gid, gt);
+            }
         }
         if (!last) {
             if (cf_row && gt == 0) tma_store_wait_read();   // the staging buffer is rewritten by the next step
@@ -1045,6 +1088,7 @@ cudaError_t launch_env(const msat_plan* plan, EnvMode mode, const EnvArgs& a0, c
     if (a.num_steps < 1) a.num_steps = 1;
     const bool noobs = a.obs == nullptr;
     a.L = noobs ? plan->layout_noobs : plan->layout_obs;
+    a.obs_i8 = plan->obs_i8;
     const int gs = noobs ? plan->group_threads_noobs : plan->group_threads;
     const int smem = noobs ? plan->smem_bytes_noobs : plan->smem_bytes;
     if (noobs) {

@@ -86,7 +86,8 @@ def create_agent_groups(num_vars: int, vars_per_agent: Optional[int], verbose: b
 class _Plan:
     """RAII holder of an ``msat_plan*``."""
 
-    def __init__(self, n, m, k, A, action_mode, max_steps, group_threads=0, reward=None, incremental=False):
+    def __init__(self, n, m, k, A, action_mode, max_steps, group_threads=0, reward=None, incremental=False,
+                 obs_int8=False):
         self._lib = _lib.load()
         h = C.c_void_p()
         _lib.check(self._lib.msat_plan_create(C.byref(h), n, m, k, A, action_mode, max_steps, group_threads),
@@ -96,6 +97,8 @@ class _Plan:
             _lib.check(self._lib.msat_plan_set_reward(h, *reward), "msat_plan_set_reward")
         if incremental:             # before any bank / state is sized from the dims
             _lib.check(self._lib.msat_plan_set_clause_update(h, 1), "msat_plan_set_clause_update")
+        if obs_int8:
+            _lib.check(self._lib.msat_plan_set_obs_dtype(h, 1), "msat_plan_set_obs_dtype")
         self.dims = _lib.Dims()
         _lib.check(self._lib.msat_plan_dims(h, C.byref(self.dims)), "msat_plan_dims")
 
@@ -215,8 +218,15 @@ class SATEnv:
     def __init__(self, num_vars, num_clauses, max_steps: int, vars_per_agent: Optional[int] = None,
                  action_mode: int = 0, r_clause: float = 0.02, r_sat: float = 1.0, gamma: float = 0.99,
                  *, device: Union[str, torch.device, None] = None, verbose: bool = True,
-                 group_threads: int = 0, reward_mode: str = "sparse", clause_update: str = "full"):
+                 group_threads: int = 0, reward_mode: str = "sparse", clause_update: str = "full",
+                 obs_dtype: Union[str, torch.dtype] = torch.int32):
         self._lib = _lib.load()
+        # int32 is what the reference declares (env:390-396) and the default; int8 carries the same -1 / 0 / 1
+        # values in a quarter of the bytes for consumers that cast the observations anyway (MSAT_OBS_INT8)
+        obs_dtype = {"int32": torch.int32, "int8": torch.int8}.get(obs_dtype, obs_dtype)
+        if obs_dtype not in (torch.int32, torch.int8):
+            raise ValueError("obs_dtype must be torch.int32 (the reference's) or torch.int8")
+        self.obs_dtype = obs_dtype
         self.num_vars = int(num_vars)
         self.num_clauses = int(num_clauses)
         self.agent_groups = create_agent_groups(self.num_vars, vars_per_agent, verbose=verbose)
@@ -279,7 +289,8 @@ class SATEnv:
             reward = (1, float(self.gamma), float(self.r_clause), float(self.r_sat)) if self.reward_mode == "shaped" else None
             self._plans[k] = _Plan(self.num_vars, self.num_clauses, k, self.num_agents, self.action_mode,
                                    self.max_steps, self._group_threads, reward,
-                                   incremental=self.clause_update == "incremental")
+                                   incremental=self.clause_update == "incremental",
+                                   obs_int8=self.obs_dtype == torch.int8)
         return self._plans[k]
 
     def count_resets(self, k: int, counter: Optional[torch.Tensor]) -> None:
@@ -338,7 +349,7 @@ class SATEnv:
         packed = state_out if state_out is not None else torch.empty((B, d.state_words), dtype=torch.int32, device=dev)
         obs = obs_out
         if obs is None and want_obs:
-            obs = torch.empty((B, d.A, d.D), dtype=torch.int32, device=dev)
+            obs = torch.empty((B, d.A, d.D), dtype=self.obs_dtype, device=dev)
         _lib.check(self._lib.msat_reset(bank.plan.handle, _ptr(bank.data), bank.num_problems, _ptr(problem_idx),
                                         _ptr(keys), _ptr(packed), _ptr(obs), B, _stream_ptr(dev)), "msat_reset")
         return obs, SATState(self, bank, packed, True)
@@ -399,7 +410,7 @@ class SATEnv:
         else:
             dev = self._require_cuda()
             block = torch.empty(B * (4 * rc + 8 + dc + 1), dtype=torch.uint8, device=dev)
-            obs = torch.empty((B, A, D), dtype=torch.int32, device=dev) if want_obs else None
+            obs = torch.empty((B, A, D), dtype=self.obs_dtype, device=dev) if want_obs else None
         o0, o1, o2, o3 = 4 * rc * B, 4 * rc * B + 4 * B, 4 * rc * B + 8 * B, 4 * rc * B + 8 * B + dc * B
         newly = None
         if self.reward_mode == "shaped":
@@ -435,7 +446,7 @@ class SATEnv:
         dev = self._require_cuda()
         d = state.bank.plan.dims
         B = state.num_envs
-        obs = torch.empty((B, d.A, d.D), dtype=torch.int32, device=dev)
+        obs = torch.empty((B, d.A, d.D), dtype=self.obs_dtype, device=dev)
         _lib.check(self._lib.msat_get_obs(state.bank.plan.handle, _ptr(state.bank.data), state.bank.num_problems,
                                           _ptr(state.packed), _ptr(obs), B, _stream_ptr(dev)), "msat_get_obs")
         return obs

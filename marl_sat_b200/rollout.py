@@ -236,7 +236,7 @@ class VecSATEnv:
             out["gnn_assignment"] = torch.empty(lead + (d.n,), dtype=torch.int32, device=dev)
             out["gnn_clause_features"] = torch.empty(lead + (d.m, 3), dtype=torch.float32, device=dev)
         elif self.out.get("obs") is not None:
-            out["obs"] = torch.empty(lead + (d.A, d.D), dtype=torch.int32, device=dev)
+            out["obs"] = torch.empty(lead + (d.A, d.D), dtype=self.env.obs_dtype, device=dev)
         return out
 
     def steps(self, actions: torch.Tensor, out: Dict[str, torch.Tensor]) -> Dict[str, torch.Tensor]:

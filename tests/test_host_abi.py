@@ -208,7 +208,7 @@ def test_xla_ffi_shim_parses_and_covers_the_enqueue_entry_points():
             assert res.returncode == 0, res.stderr
     header = (root / "include" / "marl_sat_b200.h").read_text()
     declared = set(re.findall(r"\bint (msat_\w+)\(", header))
-    host_only = {"msat_plan_create", "msat_plan_dims", "msat_plan_set_reward", "msat_plan_set_clause_update",
+    host_only = {"msat_plan_create", "msat_plan_dims", "msat_plan_set_reward", "msat_plan_set_clause_update", "msat_plan_set_obs_dtype",
                  "msat_plan_set_reset_counter", "msat_tune", "msat_dimacs_parse", "msat_shutdown", "msat_host_pipe_create",
                  "msat_host_wait", "msat_rollout_step_host", "msat_rollout_step_host_async"}
     # single-step entry points are the K = 1 case of msat_rollout_steps, which the shim binds

@@ -319,3 +319,42 @@ def test_problem_index_validation():
     with pytest.raises(IndexError):
         env.reset_from_bank(bank, torch.tensor([0, -1, 1], dtype=torch.int32), keys, validate_indices=True)
     env.reset_from_bank(bank, torch.tensor([0, 3, 1], dtype=torch.int32), keys, validate_indices=True)
+
+
+# ---------------------------------------------------------------------------------------------------------
+# MSAT_OBS_INT8: the same observations in one byte per element
+# ---------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("n,m,k,vpa,kind,gs,B", [
+    (20, 91, 3, None, "uniform", 0, 77),        # half-warp groups, 655-element rows (odd: every 16-byte phase)
+    (20, 91, 3, None, "uniform", 32, 5),
+    (7, 12, 3, None, "uniform", 0, 33),         # rows shorter than one 16-byte chunk pair
+    (3, 2, 2, 1, "uniform", 0, 19),             # an env's whole range is shorter than one chunk
+    (50, 218, 3, None, "uniform", 0, 41),
+    (50, 218, 3, None, "uniform", 64, 9),
+    (100, 430, 7, 7, "mixed", 0, 13),           # 128-thread groups
+    (100, 430, 3, None, "uniform", 0, 11),      # 256-thread groups
+])
+def test_int8_observations_equal_int32(n, m, k, vpa, kind, gs, B):
+    M = _msat()
+    P, K = 6, 5
+    problems = _formulas(kind, P, n, m, k, seed=n + B)
+    key0 = otf.prng_key(n)
+    envs = [M.SATEnv(n, m, 3, vars_per_agent=vpa, verbose=False, group_threads=gs, obs_dtype=dt)
+            for dt in (torch.int32, torch.int8)]
+    vecs = [M.VecSATEnv(e, problems, B, key0) for e in envs]
+    o32, o8 = (v.reset() for v in vecs)
+    assert o8.dtype == torch.int8 and o32.dtype == torch.int32 and torch.equal(o8.to(torch.int32), o32)
+    rng = np.random.default_rng(B)
+    for t in range(4):                           # max_steps = 3: auto-resets inside
+        acts = torch.from_numpy(_actions(rng, envs[0], (B,))).cuda()
+        a, b = (v.step(acts) for v in vecs)
+        assert torch.equal(b["obs"].to(torch.int32), a["obs"]), t
+        assert torch.equal(a["reward"], b["reward"]) and torch.equal(a["done"], b["done"])
+    table = torch.from_numpy(_actions(rng, envs[0], (K, B))).cuda()
+    outs = [v.alloc_multi_step_outputs(K, emit_every_step=True) for v in vecs]
+    for v, o in zip(vecs, outs):
+        v.steps(table, o)
+    assert outs[1]["obs"].dtype == torch.int8 and torch.equal(outs[1]["obs"].to(torch.int32), outs[0]["obs"])
+    assert torch.equal(vecs[0].state, vecs[1].state)
+    g32, g8 = (e.get_obs_array(v.sat_state()) for e, v in zip(envs, vecs))
+    assert g8.dtype == torch.int8 and torch.equal(g8.to(torch.int32), g32)
