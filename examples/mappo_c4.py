@@ -40,6 +40,8 @@ def main():
     ap.add_argument("--minibatch", type=int, default=16384, help="env-steps per minibatch per rank")
     ap.add_argument("--updates", type=int, default=2)
     ap.add_argument("--hidden", type=int, default=128)
+    ap.add_argument("--obs-int8", action="store_true",
+                    help="int8 observations (MSAT_OBS_INT8): same values, a quarter of the bytes the policy reads")
     args = ap.parse_args()
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -50,7 +52,8 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
-    env = M.SATEnv(args.n, args.m, args.max_steps, verbose=False, device=dev)
+    env = M.SATEnv(args.n, args.m, args.max_steps, verbose=False, device=dev,
+                   obs_dtype=torch.int8 if args.obs_int8 else torch.int32)
     problems = synth.uniform_ksat_torch(args.problems, args.n, args.m, 3, seed=20261018 + 4, device=dev)
     bank = env.make_bank(problems, validate=False)
     vec = M.VecSATEnv(env, bank, args.envs, M.prng_key(42), world_size=world, rank=rank, compact_outputs=True)
