@@ -125,7 +125,14 @@ int finish_plan(msat_plan* p) {
     // spot -- larger groups idle most lanes in the short per-env phases, smaller ones serialise the stores
     // -- and below ~450 chunks (uf20-91: 164, uf35-149: 384) two envs share a warp (half-warp groups): the fixed
     // per-env instruction count, not the stores, bounds those shapes (profiles/r2_group_size_sweep.md)
-    if (gs == 0) gs = chunks <= 448 ? 16 : (chunks <= 768 ? 32 : (chunks <= 1536 ? 64 : (chunks <= 3072 ? 128 : 256)));
+    if (gs == 0) gs = chunks <= 448 ? 16 : (chunks <= 768 ? 32 : (chunks <= 1536 ? 64 : (chunks <= 2048 ? 128 : 256)));
+    if (p->requested_group_threads == 0 && p->obs_i8) {
+        // int8 observations: a quarter of the store trips for the same per-env set-up, so smaller groups win
+        // (uf100-430 x 65,536: 0.266 / 0.271 / 0.299 / 0.365 ms with 32 / 64 / 128 / 256 threads per env)
+        // rule from the sweep in profiles/r2_group_size_sweep.md: store chunks plus a quarter of the literal count
+        const int w8 = (d.AD + 15) / 16 + (m * k) / 4;
+        gs = w8 <= 300 ? 16 : (w8 <= 1320 ? 32 : (w8 <= 1800 ? 64 : (w8 <= 4096 ? 128 : 256)));
+    }
     if (gs != 16 && gs != 32 && gs != 64 && gs != 128 && gs != 256) return MSAT_EINVAL;
     const GroupLayout L = group_layout(d, true);
     const int kChain = 40 * kMaxFusedSteps;      // room for the K key chains of a multi-step launch
@@ -148,7 +155,6 @@ int finish_plan(msat_plan* p) {
     p->smem_bytes_noobs = Ln.total * (kCtaThreads / gn);
     p->compile_smem_bytes = 4 * (m + n) * d.agw + (d.cnt_words ? 4 * (n + 1) : 0);
     if (p->compile_smem_bytes > kMaxSmem) return MSAT_EUNSUPPORTED;
-    (void)k;
     return MSAT_OK;
 }
 
@@ -213,8 +219,14 @@ int msat_plan_set_reward(msat_plan* plan, int32_t mode, double gamma, double r_c
 
 int msat_plan_set_obs_dtype(msat_plan* plan, int32_t dtype) {
     if (!plan || (dtype != MSAT_OBS_INT32 && dtype != MSAT_OBS_INT8)) return MSAT_EINVAL;
+    const int old = plan->obs_i8;
     plan->obs_i8 = dtype == MSAT_OBS_INT8;
-    return MSAT_OK;
+    const int rc = finish_plan(plan);          // the group size follows the store width
+    if (rc != MSAT_OK) {
+        plan->obs_i8 = old;
+        finish_plan(plan);
+    }
+    return rc;
 }
 
 int msat_plan_set_clause_update(msat_plan* plan, int32_t mode) {

@@ -181,7 +181,7 @@ def test_plan_groups_for_baseline_shapes():
     """Group sizes chosen by msat_plan_create for the BASELINE shapes (profiles/r1_group_size_sweep.md,
     profiles/r2_group_size_sweep.md): half-warp groups (two envs per warp) for the smallest observations."""
     expect = {(20, 91, None): 16, (50, 218, None): 32, (100, 430, None): 256, (250, 1065, None): 256,
-              (100, 430, 7): 128, (35, 149, 7): 16}
+              (100, 430, 7): 256, (35, 149, 7): 16}
     for (n, m, vpa), gs in expect.items():
         env = M.SATEnv(n, m, 512, vars_per_agent=vpa, verbose=False, device="cpu")
         assert env._plan_for(3).dims.group_threads == gs, (n, m, vpa)
