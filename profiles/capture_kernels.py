@@ -67,6 +67,13 @@ if "incr" in which:
     for i in range(3):
         vi.step(acts[i])
     del vi, bank_i
+if "i8" in which:
+    env8 = M.SATEnv(n, m, 512, verbose=False, device=dev, obs_dtype=torch.int8)
+    v8 = M.VecSATEnv(env8, bank.for_env(env8), B, M.prng_key(1))
+    v8.reset()
+    for i in range(3):
+        v8.step(acts[i])
+    del v8
 if "shapes" in which:
     # one observation-writing step launch per (workload, per-GPU batch) for profiles/traffic.json
     SHAPES = [("uf100-430", 100, 430, 3, None, "uniform", bs) for bs in (32768, 16384, 8192)] + [
