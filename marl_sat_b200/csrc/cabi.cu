@@ -417,7 +417,7 @@ int msat_rollout_step_host(const msat_plan* plan, const void* bank, int32_t P, u
     cudaStream_t s = (cudaStream_t)stream;
     const Dims& d = plan->d;
     const size_t act_per_env = (size_t)d.A * (d.action_mode == 0 ? 1 : d.V);
-    const size_t obs_per_env = (size_t)d.A * d.D;
+    const size_t obs_env_bytes = (size_t)d.A * d.D * (plan->obs_i8 ? 1u : 4u);   // int8 plans: one byte per element
     const ResultBufs rb{reward_dev, reward_cols, done_dev, done_cols, solved_dev, num_unsatisfied_dev, episode_step_dev,
                         reward_host, done_host, solved_host, num_unsatisfied_host, episode_step_host};
 
@@ -430,7 +430,9 @@ int msat_rollout_step_host(const msat_plan* plan, const void* bank, int32_t P, u
         if (e != cudaSuccess) return (int)e;
         uint32_t* st = state + (size_t)b0 * d.state_words;
         int rc = msat_rollout_step(plan, bank, P, st, st, actions_dev + b0 * act_per_env, rng_in, chain_out, Bg,
-                                   env_offset + b0, obs_dev ? obs_dev + b0 * obs_per_env : nullptr,
+                                   env_offset + b0,
+                                   obs_dev ? reinterpret_cast<int32_t*>(reinterpret_cast<char*>(obs_dev) + b0 * obs_env_bytes)
+                                           : nullptr,
                                    reward_dev ? reward_dev + (size_t)b0 * reward_cols : nullptr, reward_cols,
                                    done_dev ? done_dev + (size_t)b0 * done_cols : nullptr, done_cols,
                                    solved_dev ? solved_dev + b0 : nullptr,

@@ -285,12 +285,14 @@ def test_baseline_sizes_rollout_subsample_matches_oracle(name, n, m, k, vpa, kin
     assert np.array_equal(to_np(st.variable_assignments[sub]), st_r.variable_assignments)
 
 
-def test_sliced_host_step_at_headline_shape():
-    """msat_rollout_step_host's four-slice two-stream path on uf100-430 (the headline shape, 256-thread groups)."""
+@pytest.mark.parametrize("obs_dtype", [torch.int32, torch.int8])
+def test_sliced_host_step_at_headline_shape(obs_dtype):
+    """msat_rollout_step_host's four-slice two-stream path on uf100-430 (the headline shape, 256-thread groups;
+    with int8 observations the slices' observation offsets are in bytes)."""
     M = _msat()
     n, m, B, P = 100, 430, 33001, 32
     problems = _formulas("uniform", P, n, m, 3, seed=2)
-    env = M.SATEnv(n, m, 3, verbose=False)
+    env = M.SATEnv(n, m, 3, verbose=False, obs_dtype=obs_dtype)
     bank = env.make_bank(problems)
     key0 = otf.prng_key(8)
     dev_vec = M.VecSATEnv(env, bank, B, key0, compact_outputs=True)
