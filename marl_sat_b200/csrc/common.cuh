@@ -124,6 +124,63 @@ __host__ __device__ __forceinline__ void env_reset_key(uint32_t rk0, uint32_t rk
     key[1] = bits32_at(rk0, rk1, 2u * Bg, 2u * g + 1u);
 }
 
+#ifdef __CUDACC__
+// The same derivation for ONE env spread over four consecutive lanes (`lane4` = 0..3 within `mask`): the thirteen
+// Threefry blocks of  chain -> (prob_key, reset_key) -> (problem index, reset key)  form five dependent levels, and
+// the blocks of a level run on different lanes (branch-free: a diverging warp would run them one after the other).
+//   level 1-2: split(rng), split(rng)            two blocks each (lanes 0,1)
+//   level 3:   split(rng, 3)                     three blocks (lanes 0,1,2)
+//   level 4:   split(prob_key) (lanes 0,1)  +  the two words of split(reset_key, Bg)[g] (lanes 2,3)
+//   level 5:   the high / low draws of randint(prob_key, (Bg,), 0, P)[g] (lanes 0,1)
+// have_chain: prob_key / reset_key are already known (c6..c9), levels 1-3 are skipped.  Every lane of `mask` must
+// call; all of them return the same results.
+__device__ __forceinline__ void env_reset_inputs_4lanes(uint32_t mask, int lane4, int base_lane, bool have_chain,
+                                                        uint32_t r0, uint32_t r1, uint32_t c6, uint32_t c7, uint32_t c8,
+                                                        uint32_t c9, uint32_t Bg, uint32_t g, uint32_t P,
+                                                        uint32_t& pidx, uint32_t& key0, uint32_t& key1) {
+    uint32_t x0, x1;
+    if (!have_chain) {
+        for (int lvl = 0; lvl < 2; ++lvl) {                      // rng <- split(rng)[0]: blocks (0,2), (1,3)
+            x0 = (uint32_t)(lane4 & 1);
+            x1 = 2u + (uint32_t)(lane4 & 1);
+            threefry2x32(r0, r1, x0, x1);
+            r0 = __shfl_sync(mask, x0, base_lane);
+            r1 = __shfl_sync(mask, x0, base_lane + 1);
+        }
+        const uint32_t i = lane4 < 3 ? (uint32_t)lane4 : 0u;     // split(rng, 3): blocks (0,3), (1,4), (2,5)
+        x0 = i;
+        x1 = 3u + i;
+        threefry2x32(r0, r1, x0, x1);
+        c7 = __shfl_sync(mask, x1, base_lane);                   // prob_key = {z0, x1(block 0)}
+        c8 = __shfl_sync(mask, x1, base_lane + 1);               // reset_key = {y1, z1}
+        c6 = __shfl_sync(mask, x0, base_lane + 2);
+        c9 = __shfl_sync(mask, x1, base_lane + 2);
+    }
+    // level 4: lanes 0,1 -> block lane of split(prob_key); lanes 2,3 -> word (lane - 2) of split(reset_key, Bg)[g]
+    const bool upper = lane4 >= 2;
+    const uint32_t N2 = 2u * Bg, half2 = (N2 + 1u) >> 1;
+    const uint32_t i2 = 2u * g + (uint32_t)(lane4 & 1);
+    const bool lo2 = i2 < half2;
+    const uint32_t blk2 = lo2 ? i2 : i2 - half2;
+    x0 = upper ? blk2 : (uint32_t)(lane4 & 1);
+    x1 = upper ? ((half2 + blk2 < N2) ? half2 + blk2 : 0u) : 2u + (uint32_t)(lane4 & 1);
+    threefry2x32(upper ? c8 : c6, upper ? c9 : c7, x0, x1);
+    const uint32_t word = lo2 ? x0 : x1;
+    key0 = __shfl_sync(mask, word, base_lane + 2);
+    key1 = __shfl_sync(mask, word, base_lane + 3);
+    const uint32_t k10 = __shfl_sync(mask, x0, base_lane), k11 = __shfl_sync(mask, x0, base_lane + 1);   // k1 = a
+    const uint32_t k20 = __shfl_sync(mask, x1, base_lane), k21 = __shfl_sync(mask, x1, base_lane + 1);   // k2 = b
+    // level 5: lane 0 (and 2) draws the high word from k1, lane 1 (and 3) the low word from k2
+    const bool odd = (lane4 & 1) != 0;
+    const uint32_t v = bits32_at(odd ? k20 : k10, odd ? k21 : k11, Bg, g);
+    const uint32_t hi = __shfl_sync(mask, v, base_lane), lo = __shfl_sync(mask, v, base_lane + 1);
+    const uint32_t span = P > 0u ? P : 1u;
+    uint32_t mult = 65536u % span;
+    mult = (mult * mult) % span;
+    pidx = ((hi % span) * mult + (lo % span)) % span;
+}
+#endif
+
 // ---- bit-stream helpers ------------------------------------------------------
 // 32 bits starting at bit `pos` of a clean little-endian bit array of `nwords` words
 // (bits past the logical end are zero; reads outside the array return zero).  pos may be negative.

@@ -948,17 +948,24 @@ __global__ void __launch_bounds__(kCtaThreads, (MULTI || !OBS) ? 4 : 8) env_kern
                 uint32_t rk0, rk1;
                 if (a.rng_in) {
                     // fused key derivation (learner:426-434) from the rollout rng, global env index
-                    if (gt == 0) {
-                        uint32_t c[10], k[2];
+                    // the first four lanes of the group share the Threefry blocks (five dependent levels
+                    // instead of thirteen blocks on one thread while the rest of the group waits)
+                    if (gt < 4) {
+                        const int base_lane = GS < 32 ? (int)(threadIdx.x & 31u & (32u - GS)) : 0;
+                        uint32_t c6 = 0u, c7 = 0u, c8 = 0u, c9 = 0u, r0 = 0u, r1 = 0u, np, k0, k1;
                         if (MULTI) {
-                            for (int i = 6; i < 10; ++i) c[i] = s_chain[10 * j + i];
+                            c6 = s_chain[10 * j + 6]; c7 = s_chain[10 * j + 7];
+                            c8 = s_chain[10 * j + 8]; c9 = s_chain[10 * j + 9];
                         } else {
-                            rng_chain_compute(a.rng_in[0], a.rng_in[1], c);
+                            r0 = a.rng_in[0]; r1 = a.rng_in[1];
                         }
-                        misc[1] = (int)env_problem_index(c[6], c[7], a.Bg, a.env_off + (uint32_t)e, (uint32_t)a.P);
-                        env_reset_key(c[8], c[9], a.Bg, a.env_off + (uint32_t)e, k);
-                        misc[2] = (int)k[0];
-                        misc[3] = (int)k[1];
+                        env_reset_inputs_4lanes(0xFu << base_lane, gt, base_lane, MULTI, r0, r1, c6, c7, c8, c9, a.Bg,
+                                                a.env_off + (uint32_t)e, (uint32_t)a.P, np, k0, k1);
+                        if (gt == 0) {
+                            misc[1] = (int)np;
+                            misc[2] = (int)k0;
+                            misc[3] = (int)k1;
+                        }
                     }
                     group_sync<GS>(gid);
                     pidx = misc[1];
