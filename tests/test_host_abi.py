@@ -215,3 +215,23 @@ def test_xla_ffi_shim_parses_and_covers_the_enqueue_entry_points():
     covered_by = {"msat_rollout_step": "msat_rollout_steps", "msat_rollout_step_gnn": "msat_rollout_steps"}
     for fn in sorted(declared - host_only):
         assert covered_by.get(fn, fn) + "(" in text, f"{fn} has no FFI handler"
+
+
+def test_obs_dtype_option_and_its_group_sizes():
+    """MSAT_OBS_INT8 is opt-in, validated, and re-tunes the group size (a quarter of the store trips)."""
+    import pytest
+    import torch
+    with pytest.raises(ValueError):
+        M.SATEnv(20, 91, 8, verbose=False, device="cpu", obs_dtype=torch.float32)
+    expect = {(100, 430, None, 3): (256, 32), (250, 1065, None, 3): (256, 128), (100, 430, 7, 7): (256, 64),
+              (20, 91, None, 3): (16, 16)}          # (n, m, vars per agent, literals per clause)
+    for (n, m, vpa, k), (gs32, gs8) in expect.items():
+        e32 = M.SATEnv(n, m, 512, vars_per_agent=vpa, verbose=False, device="cpu")
+        e8 = M.SATEnv(n, m, 512, vars_per_agent=vpa, verbose=False, device="cpu", obs_dtype="int8")
+        assert e32.obs_dtype == torch.int32 and e8.obs_dtype == torch.int8
+        assert e32._plan_for(k).dims.group_threads == gs32 and e8._plan_for(k).dims.group_threads == gs8, (n, m, vpa)
+    pinned = M.SATEnv(100, 430, 512, verbose=False, device="cpu", obs_dtype="int8", group_threads=128)
+    assert pinned._plan_for(3).dims.group_threads == 128
+    lib = _lib.load()
+    assert lib.msat_plan_set_obs_dtype(None, 0) == _lib.MSAT_EINVAL
+    assert lib.msat_plan_set_obs_dtype(pinned._plan_for(3).handle, 7) == _lib.MSAT_EINVAL
