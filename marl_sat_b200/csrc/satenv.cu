@@ -547,8 +547,8 @@ __device__ __forceinline__ uint32_t expand_nibble_i8(uint32_t mn, uint32_t xn) {
 }
 
 // I8 (msat_plan_set_obs_dtype): the same flat range with one byte per element -- `obs` then points to int8 data,
-// a 32-byte chunk (one 256-bit store) covers the 32 elements of one mask / value word pair and at most 31 bytes at
-// each end of an env's range go out as scalar byte stores.
+// a 16-byte chunk covers 16 elements (half a mask / value word pair) and at most 15 bytes at each end of an
+// env's range go out as scalar byte stores.
 template <int GS, bool I8>
 __device__ __forceinline__ void emit_obs(const Dims& d, long long row, const uint32_t* assign, const uint32_t* satw,
                                          uint32_t* X, uint2* smx, const uint32_t* mflat,
@@ -598,27 +598,28 @@ __device__ __forceinline__ void emit_obs(const Dims& d, long long row, const uin
     group_sync<GS>(gid);
 
     if constexpr (I8) {
-        // ---- int8: one 256-bit store (STG.256) per 32 elements = one {mask, value} word pair, 32-byte aligned base
+        // ---- int8: chunk q covers elements [16q, 16q+16) of the re-based range (32-byte aligned base) ----
         int8_t* out8 = reinterpret_cast<int8_t*>(obs) + (g_start - s);
         const int lo = s, hi = s + d.AD;
-        const int q_lo = (lo + 31) >> 5, q_hi = hi >> 5;      // word pairs that lie completely inside the env's range
+        const int q_lo = (lo + 15) >> 4, q_hi = hi >> 4;
         {
-            const uint2* sp = smx + q_lo + gt;
-            int8_t* op = out8 + 32 * (q_lo + gt);
+            int q = q_lo + gt;                      // GS is even: a lane keeps the same half of its word pair
+            const int sh = (q & 1) * 16;
+            const uint2* sp = smx + (q >> 1);
+            uint4* op = reinterpret_cast<uint4*>(out8) + q;
 #pragma unroll 2
-            for (int q = q_lo + gt; q < q_hi; q += GS, sp += GS, op += 32 * GS) {
+            for (; q < q_hi; q += GS, sp += GS / 2, op += GS) {
                 const uint2 mx = *sp;
-                uint32_t v[8];
-#pragma unroll
-                for (int i = 0; i < 8; ++i) v[i] = expand_nibble_i8((mx.x >> (4 * i)) & 0xFu, (mx.y >> (4 * i)) & 0xFu);
-                asm volatile("st.global.cs.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(op), "r"(v[0]), "r"(v[1]),
-                             "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7])
-                             : "memory");
+                const uint32_t m16 = mx.x >> sh, x16 = mx.y >> sh;
+                __stcs(op, make_uint4(expand_nibble_i8(m16 & 0xFu, x16 & 0xFu),
+                                      expand_nibble_i8((m16 >> 4) & 0xFu, (x16 >> 4) & 0xFu),
+                                      expand_nibble_i8((m16 >> 8) & 0xFu, (x16 >> 8) & 0xFu),
+                                      expand_nibble_i8((m16 >> 12) & 0xFu, (x16 >> 12) & 0xFu)));
             }
         }
-        // the < 32 elements before the first / after the last complete pair (or the whole range when it is short)
-        const int head_end = min(32 * q_lo, hi);
-        const int tail_start = max(32 * q_hi, head_end);
+        // the < 16 elements before the first / after the last complete chunk (or the whole range when it is short)
+        const int head_end = min(16 * q_lo, hi);
+        const int tail_start = max(16 * q_hi, head_end);
         auto put = [&](int i) {
             const uint2 mx = smx[i >> 5];
             out8[i] = ((mx.x >> (i & 31)) & 1u) ? (int8_t)((mx.y >> (i & 31)) & 1u) : (int8_t)-1;
